@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures under tests/golden/ by RUNNING THE REFERENCE.
+
+Runs only in the dev container (needs /root/reference).  The reference's Python is
+imported unmodified from /root/reference/bruce_slam/src; what is missing in this
+image is stubbed *around* it, never inside it:
+
+  * ROS / gtsam / matplotlib / shapely imports  -> auto-generated stub modules
+    (they are plumbing: subscribers, publishers, message types, plotting);
+  * bruce_slam.cfar (pybind module built from cpp/cfar.cpp) -> a thin module over
+    oracle/_ref/libcfar_ref.so, i.e. the UNMODIFIED cfar.cpp compiled against the
+    storage-only Eigen shim (oracle/Makefile);
+  * bruce_slam.pcl (libpointmatcher / PCL wrapper) -> identity stand-ins, so that
+    the fixture captures the cloud BEFORE pcl.downsample / pcl.remove_outlier
+    (those two are third-party arithmetic -- "parity unpinned").
+
+Fixtures written:
+  tests/golden/cfar_tau.json        threshold factors from the reference's CFAR.py
+                                    (CFAR.py:71-121) for several (Ntc,Ngc,Pfa,rank)
+  tests/golden/cfar_masks.npz       packed CFAR masks (+ a threshold-image digest) of
+                                    the config-1 frame from the reference cfar.cpp
+  tests/golden/featx_config1.npz    FeatureExtraction.callback on the config-1 ping:
+                                    map_x/map_y digests + samples, Cartesian (row,col)
+                                    list and the metric points it publishes
+"""
+import hashlib
+import importlib
+import importlib.abc
+import importlib.machinery
+import json
+import os
+import sys
+import types
+from unittest import mock
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SRC = "/root/reference/bruce_slam/src"
+sys.path.insert(0, REPO)
+
+STUB_ROOTS = {
+    "rospy", "gtsam", "cv_bridge", "sensor_msgs", "geometry_msgs", "ros_numpy", "matplotlib",
+    "shapely", "std_msgs", "visualization_msgs", "rti_dvl", "bar30_depth", "sonar_oculus", "tf",
+    "message_filters", "nav_msgs", "rosbag", "kvh_gyro", "tf2_ros", "std_srvs", "bruce_msgs",
+}
+
+
+class _StubModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        m = mock.MagicMock(name=f"{self.__name__}.{name}")
+        setattr(self, name, m)
+        return m
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path, target=None):
+        if fullname.split(".")[0] in STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _StubModule(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def _install_reference():
+    from oracle import oracle as orc
+
+    sys.meta_path.insert(0, _StubFinder())
+    sys.path.insert(0, REF_SRC)
+    pkg = importlib.import_module("bruce_slam")
+
+    cfar = types.ModuleType("bruce_slam.cfar")
+
+    def _mk(alg, two):
+        def f(img, train_hs, guard_hs, *rest):
+            if alg == 3:
+                k, tau = rest
+            else:
+                (tau,), k = rest, 0
+            mask, thr = orc.cfar_reference(alg, np.asarray(img, np.float32), train_hs, guard_hs, int(k), float(tau), want_thr=two)
+            return (mask, thr) if two else mask
+        return f
+
+    for i, nm in enumerate(["ca", "soca", "goca", "os"]):
+        setattr(cfar, nm, _mk(i, False))
+        setattr(cfar, nm + "2", _mk(i, True))
+    sys.modules["bruce_slam.cfar"] = cfar
+    pkg.cfar = cfar
+
+    pcl = types.ModuleType("bruce_slam.pcl")
+    pcl.downsample = lambda pts, *a: pts
+    pcl.remove_outlier = lambda pts, *a: pts
+    sys.modules["bruce_slam.pcl"] = pcl
+    pkg.pcl = pcl
+    return pkg
+
+
+def _digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    from sonar_slam_b200 import synth
+
+    out = os.path.join(REPO, "tests", "golden")
+    os.makedirs(out, exist_ok=True)
+    _install_reference()
+    from bruce_slam.CFAR import CFAR  # the reference's own class
+
+    # ---- threshold factors -------------------------------------------------------
+    taus = []
+    for (Ntc, Ngc, Pfa, rank) in [(40, 10, 0.1, 10), (40, 10, 1e-2, None), (24, 4, 0.05, 6),
+                                   (16, 8, 1e-3, 15), (40, 10, 0.1, 0), (8, 2, 0.2, 3)]:
+        try:
+            c = CFAR(Ntc, Ngc, Pfa, rank)
+        except ValueError as e:  # the reference itself gives up on some parameter sets
+            taus.append(dict(Ntc=Ntc, Ngc=Ngc, Pfa=Pfa, rank=rank, raises=str(e)))
+            continue
+        taus.append(dict(Ntc=Ntc, Ngc=Ngc, Pfa=Pfa, rank=rank,
+                         CA=float(c.threshold_factor_CA), SOCA=float(c.threshold_factor_SOCA),
+                         GOCA=float(c.threshold_factor_GOCA), OS=float(c.threshold_factor_OS),
+                         str=str(c)))
+    with open(os.path.join(out, "cfar_tau.json"), "w") as f:
+        json.dump(taus, f, indent=1)
+
+    # ---- CFAR masks of the config-1 frame through the reference's CFAR class -----
+    img = synth.make_frame(seed=1)
+    det = CFAR(40, 10, 0.1, 10)
+    masks = {}
+    for alg in ["CA", "SOCA", "GOCA", "OS"]:
+        m = det.detect(img, alg)
+        m2, thr = det.detect2(img, alg)
+        assert np.array_equal(m, m2)
+        masks[alg] = np.packbits(np.ascontiguousarray(m))
+        masks[alg + "_count"] = np.int64(m.sum())
+        masks[alg + "_thr_sha256"] = np.array(_digest(np.ascontiguousarray(thr)))
+        masks[alg + "_thr_sample"] = np.ascontiguousarray(thr)[::37, ::41].copy()
+    np.savez_compressed(os.path.join(out, "cfar_masks.npz"), **masks)
+
+    # ---- FeatureExtraction.callback on the config-1 ping --------------------------
+    fe_mod = importlib.import_module("bruce_slam.feature_extraction")
+    res = {}
+    for tag, bearings in [("uniform", synth.bearings_uniform(512)), ("oculus", synth.bearings_oculus(512))]:
+        fe = fe_mod.FeatureExtraction()
+        fe.Ntc, fe.Ngc, fe.Pfa, fe.rank, fe.alg = 40, 10, 0.1, 10, "SOCA"
+        fe.threshold, fe.resolution, fe.skip = 65, 0.5, 1
+        fe.outlier_filter_radius, fe.outlier_filter_min_points = 1.0, 5
+        fe.compressed_images = False
+        fe.feature_img_pub = mock.MagicMock()
+        fe.configure()
+        captured = {}
+        fe.publish_features = lambda ping, pts: captured.__setitem__("pts", np.array(pts))
+        ping = synth.Ping(ping_id=0, image=img, range_resolution=30.0 / 512, num_ranges=512,
+                          bearings=bearings)
+        msg = types.SimpleNamespace(ping_id=0, ping=img, range_resolution=ping.range_resolution,
+                                    num_ranges=512, bearings=list(bearings), header=mock.MagicMock())
+        with mock.patch.object(fe_mod.ros_numpy.image, "image_to_numpy", lambda x: x):
+            fe.callback(msg)
+        pts = captured["pts"]
+        # recover (row, col) exactly as the callback derived the points from them
+        import cv2
+        peaks = det.detect(img, "SOCA")
+        peaks &= img > 65
+        cart = cv2.remap(peaks, fe.map_x, fe.map_y, cv2.INTER_LINEAR)
+        locs = np.c_[np.nonzero(cart)]
+        res[tag + "_rows_cols"] = np.array([fe.rows, fe.cols], np.int64)
+        res[tag + "_width_height_res"] = np.array([fe.width, fe.height, fe.res], np.float64)
+        res[tag + "_map_x_sha256"] = np.array(_digest(fe.map_x))
+        res[tag + "_map_y_sha256"] = np.array(_digest(fe.map_y))
+        res[tag + "_map_x_sample"] = fe.map_x[::31, ::29].copy()
+        res[tag + "_map_y_sample"] = fe.map_y[::31, ::29].copy()
+        res[tag + "_locs"] = locs.astype(np.int32)
+        res[tag + "_points"] = pts.astype(np.float64)
+        assert len(locs) == len(pts)
+        print(tag, "rows/cols", fe.rows, fe.cols, "polar det", int(peaks.sum()), "cart px", len(locs))
+    np.savez_compressed(os.path.join(out, "featx_config1.npz"), **res)
+    print("golden fixtures written to", out)
+
+
+if __name__ == "__main__":
+    main()
