@@ -52,10 +52,11 @@ typedef struct sfe_ctx sfe_ctx; /* one GPU + one stream + scratch memory; not th
 SFE_API int sfe_version(void);
 SFE_API const char *sfe_last_error(void);
 
-/* Create a context on `device`.  `cuda_stream` may be NULL (the library creates its
- * own non-blocking stream) or a cudaStream_t owned by the caller (e.g. torch's
- * current stream), in which case all work is enqueued there. */
-SFE_API int sfe_ctx_create(int device, void *cuda_stream, sfe_ctx **out);
+/* Create a context on `device`.  own_stream != 0: the library creates its own
+ * non-blocking stream (cuda_stream is ignored).  own_stream == 0: all work is enqueued
+ * on the caller's cudaStream_t `cuda_stream` (NULL = the legacy default stream; pass
+ * e.g. torch's current stream). */
+SFE_API int sfe_ctx_create(int device, void *cuda_stream, int own_stream, sfe_ctx **out);
 SFE_API void sfe_ctx_destroy(sfe_ctx *ctx);
 SFE_API int sfe_sync(sfe_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py: gpu_launches) */

@@ -36,7 +36,7 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
         lib.sfe_version.restype = c_int
         lib.sfe_last_error.restype = ctypes.c_char_p
-        lib.sfe_ctx_create.argtypes = [c_int, c_void_p, ctypes.POINTER(c_void_p)]
+        lib.sfe_ctx_create.argtypes = [c_int, c_void_p, c_int, ctypes.POINTER(c_void_p)]
         lib.sfe_ctx_destroy.argtypes = [c_void_p]
         lib.sfe_ctx_destroy.restype = None
         lib.sfe_sync.argtypes = [c_void_p]
@@ -71,11 +71,14 @@ def check(rc, what=""):
 class Context:
     """One GPU + one stream + scratch (sfe_ctx).  Not thread-safe; make one per thread."""
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream="own"):
+        """stream: "own" -> library-owned stream; otherwise a cudaStream_t integer handle of the
+        caller (0 / None = the legacy default stream, e.g. torch.cuda.current_stream().cuda_stream)."""
         self.lib = load()
         h = c_void_p()
-        check(self.lib.sfe_ctx_create(int(device), c_void_p(stream) if stream else None, ctypes.byref(h)),
-              "sfe_ctx_create")
+        own = 1 if stream == "own" else 0
+        sp = None if (own or not stream) else c_void_p(int(stream))
+        check(self.lib.sfe_ctx_create(int(device), sp, own, ctypes.byref(h)), "sfe_ctx_create")
         self.handle = h
         self.device = int(device)
 

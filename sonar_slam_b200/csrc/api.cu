@@ -82,7 +82,7 @@ extern "C" {
 int sfe_version(void) { return SFE_VERSION; }
 const char *sfe_last_error(void) { return g_err; }
 
-int sfe_ctx_create(int device, void *cuda_stream, sfe_ctx **out) {
+int sfe_ctx_create(int device, void *cuda_stream, int own_stream, sfe_ctx **out) {
   SFE_REQUIRE(out != nullptr, "sfe_ctx_create: null out pointer");
   *out = nullptr;
   int n = 0;
@@ -105,7 +105,7 @@ int sfe_ctx_create(int device, void *cuda_stream, sfe_ctx **out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-  if (cuda_stream) {
+  if (!own_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
   } else {
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

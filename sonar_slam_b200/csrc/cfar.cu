@@ -11,20 +11,23 @@
 //      warp streams [16 range bins x 128 beams] boxes of the frame through a
 //      4-stage shared-memory ring with TMA (cp.async.bulk.tensor + mbarrier);
 //      each of the 128 consumer threads owns ONE beam, reads every cell of its
-//      beam exactly once from shared memory and keeps the last 64 range bins in
-//      a register ring, so the leading/lagging window sums are two sliding
-//      adds + two sliding subtracts per cell and nothing is ever re-read from
-//      shared or global memory.  The 0/1 mask leaves through a double-buffered
-//      shared tile and TMA stores.  HBM traffic = the image once + the mask
-//      once (no halo: a strip spans the whole range axis).
+//      beam exactly once from shared memory and keeps the last 32 cells and the
+//      last 32 window sums in two register rings.  With W[i] = sum of the 20
+//      cells ending at range bin i, the lagging window of the cell under test r
+//      is W[r+25] and the leading window is W[r-6] = W[(r+25)-31], so one add and
+//      one subtract per cell maintain both.  Nothing is re-read from shared or
+//      global memory.  The 0/1 mask (and/or a bit plane) leaves through a
+//      double-buffered shared tile and TMA stores.  HBM traffic = the image once
+//      + the mask once (no halo: a strip spans the whole range axis).
 //
-//      Exactness: for integer-valued cells with |x| <= 65535 every float32 sum
-//      is exact whatever the order, so sliding sums equal the reference's
-//      sequential sums.  The double-precision threshold compare of cfar.cpp
-//      (`img > tau * sum / train_hs`) is decided by a float32 estimate when the
-//      cell is farther than a 1e-6 relative margin from the threshold and by the
-//      identical double expression otherwise.  A strip that sees any other
-//      value (fraction, |x| > 65535, inf, nan) raises a flag and is re-done by ...
+//      Exactness: for integer-valued cells with |x| <= 2^18 every float32 sum is
+//      exact whatever the order, so sliding sums equal the reference's sequential
+//      sums.  The double-precision compare of cfar.cpp (`img > tau * sum /
+//      train_hs`) is decided from a two-term float32 evaluation of
+//      xc - S*(c_hi + c_lo) (c_hi + c_lo = tau/div to ~2^-48), whose error is
+//      < 2e-9; cells with |xc - S*c| <= 1e-7 (about one in a million) are re-done
+//      with the reference's own double expression.  A strip that sees any other
+//      value (fraction, |x| > 2^18, inf, nan) raises a flag and is re-done by ...
 //
 //  cfar_exact_kernel      ... the general path: any train_hs/guard_hs, OS-CFAR, any
 //      float input.  It accumulates each window in the reference's order
@@ -42,16 +45,20 @@ constexpr int CF_RING = 32;   // two 32-deep register rings per thread (cells, w
 constexpr int CF_T = 20;      // train_hs of the streaming path
 constexpr int CF_G = 5;       // guard_hs of the streaming path
 constexpr int CF_HALF = CF_T + CF_G;
+constexpr int CF_SPLIT = CF_CH - (CF_HALF % CF_CH);  // step of an output block at which the input box changes (7)
+constexpr float CF_AMBIG = 1e-7f;                    // |xc - S*c| below this is decided in double
 
 struct CfarParams {
   int F, R, B, strips;
   int alg, T, G, k;
   double tau;   // threshold factor (exact compare)
   double div;   // 2*T (CA), T (SOCA/GOCA), 1 (OS)
-  float c;      // float(tau / div): float32 estimate of the threshold slope
+  float c_hi;   // float(tau / div)
+  float c_lo;   // float(tau / div - c_hi)
   int gate_on;
-  float gate_f;   // largest float g with (x > g) <=> ((double)x > gate) for every float x
+  float gate_f;   // float g with (x > g) <=> ((double)x > gate) for every float x
   double gate_d;
+  const void *img;
   uint8_t *mask;  // may be null
   float *thr;     // may be null
   uint32_t *bits; // may be null
@@ -66,36 +73,93 @@ __device__ __forceinline__ float cell_to_float(uint8_t v) {
   return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.0f;
 }
 
-// Rare path of the streaming kernel: the float32 estimate is within its own
-// uncertainty of the threshold, decide with the reference's double expression.
-__device__ __noinline__ bool cfar_exact_compare(double tau, float S, double div, float xc) {
-  return (double)xc > tau * (double)S / div;
+// The reference's arithmetic for one cell (cfar.cpp:16-25, 36-48, 59-71, 82-93), reading the
+// column straight from global memory.  `train` is OS scratch: element i at train[i * tstride].
+template <typename InT>
+__device__ bool cfar_cell_exact(const InT *__restrict__ colp, size_t B, int r, const CfarParams &p, float *train,
+                                int tstride, double *thr_out) {
+  const int T = p.T, G = p.G, half = T + G;
+  double d;
+  if (p.alg == SFE_CFAR_CA) {
+    float acc = 0.f;
+    for (int i = r - half; i <= r + half; ++i)
+      if (abs(i - r) > G) acc = __fadd_rn(acc, cell_to_float(colp[(size_t)i * B]));
+    d = p.tau * (double)acc / p.div;
+  } else if (p.alg == SFE_CFAR_OS) {
+    int n = 0;
+    for (int i = r - half; i <= r + half; ++i)
+      if (abs(i - r) > G) train[(n++) * tstride] = cell_to_float(colp[(size_t)i * B]);
+    float v = __int_as_float(0x7fc00000);
+    for (int a = 0; a < n; ++a) {  // k-th smallest by rank counting
+      const float va = train[a * tstride];
+      int less = 0, leq = 0;
+      for (int b = 0; b < n; ++b) {
+        const float vb = train[b * tstride];
+        less += vb < va;
+        leq += vb <= va;
+      }
+      if (less <= p.k && p.k < leq) {
+        v = va;
+        break;
+      }
+    }
+    d = p.tau * (double)v;
+  } else {
+    float ld = 0.f, lg = 0.f;
+    for (int i = r - half; i < r - G; ++i) ld = __fadd_rn(ld, cell_to_float(colp[(size_t)i * B]));
+    for (int i = r + G + 1; i <= r + half; ++i) lg = __fadd_rn(lg, cell_to_float(colp[(size_t)i * B]));
+    // std::min(lead, lag) / std::max(lead, lag) as written in cfar.cpp:46,69
+    const float S = (p.alg == SFE_CFAR_SOCA) ? (lg < ld ? lg : ld) : (ld < lg ? lg : ld);
+    d = p.tau * (double)S / p.div;
+  }
+  const float xc = cell_to_float(colp[(size_t)r * B]);
+  bool pass = (double)xc > d;
+  if (p.gate_on) pass = pass && ((double)xc > p.gate_d);
+  if (thr_out) *thr_out = d;
+  return pass;
+}
+
+// Rare path of the streaming kernel: this thread met a cell too close to its threshold for the
+// float32 evaluation; redo its 16 output rows with the reference's expressions.
+template <typename InT>
+__device__ __noinline__ void cfar_resolve_block(const CfarParams &p, uint8_t (*obuf_ob)[CF_W], uint32_t *pass_bits,
+                                                int f, int col, int r0, int tid) {
+  if (col >= p.B) return;
+  const InT *colp = (const InT *)p.img + (size_t)f * p.R * p.B + col;
+  uint32_t pb = 0;
+  for (int i = 0; i < CF_CH; ++i) {
+    const int r = r0 + i;
+    bool pass = false;
+    if (r >= CF_HALF && r < p.R - CF_HALF) pass = cfar_cell_exact<InT>(colp, p.B, r, p, nullptr, 0, nullptr);
+    if (obuf_ob) obuf_ob[i][tid] = pass ? 1 : 0;
+    pb |= (pass ? 1u : 0u) << i;
+  }
+  *pass_bits = pb;
 }
 
 struct CfarStep {  // per-thread streaming state (all in registers; indices are static after unrolling)
-  float xr[CF_RING];  // x[rn - a]      at slot (j - a) & 31
+  float xr[CF_RING];  // x[rn - a]      at slot (J - a) & 31
   float wr[CF_RING];  // W[rn - a] = sum of the 20 cells ending at rn - a
   float w;            // W[rn - 1]
   float bad;          // > 0 once a non-integer cell was seen
   float mx;           // max |cell|
 };
 
-// One range bin.  J = position in the 32-step unrolled body; EDGE = this 16-row block
-// touches the image border (row validity must be checked per row).
+// One range bin.  J = position in the 32-step unrolled body (I = J % 16 = output row in its block);
+// EDGE = this block touches the image border / the ends of the input (row validity is checked).
 template <typename InT, int ALG, bool WITH_THR, bool MASK, bool BITS, bool EDGE, int J>
-__device__ __forceinline__ void cfar_step(CfarStep &s, const InT (*__restrict__ tile)[CF_W],
-                                          uint8_t (*__restrict__ obuf)[CF_CH][CF_W], const CfarParams &p,
-                                          const int rn, const bool has_chunk, const int tid, const int f,
-                                          const int col0, const float c, const float gate) {
-  float xn = 0.f;
-  if (!EDGE || has_chunk) xn = cell_to_float(tile[J % CF_CH][tid]);
+__device__ __forceinline__ void cfar_step(CfarStep &s, const float xn, uint8_t (*obuf_ob)[CF_W],
+                                          const CfarParams &p, const int r, const int tid,
+                                          const int f, const int col, const float c_hi, const float c_lo,
+                                          const float gate, bool &amb, uint32_t &pass_bits) {
+  constexpr int I = J % CF_CH;
   if (sizeof(InT) == 4) {
     // integer-valued?  (x + 1.5*2^23) - 1.5*2^23 == x  <=>  x integer and |x| < 2^22
     const float rt = (xn + 12582912.0f) - 12582912.0f;
     s.bad = fmaxf(s.bad, fabsf(rt - xn));
     s.mx = fmaxf(s.mx, fabsf(xn));
   }
-  // cell under test r = rn - 25:
+  // cell under test r, newest cell rn = r + 25:
   //   lagging window r+6 .. r+25  = the 20 cells ending at rn       -> W[rn]
   //   leading window r-25 .. r-6  = the 20 cells ending at rn - 31  -> W[rn-31]
   const float x20 = s.xr[(J + CF_RING - CF_T) % CF_RING];
@@ -103,11 +167,9 @@ __device__ __forceinline__ void cfar_step(CfarStep &s, const InT (*__restrict__ 
   const float lead = s.wr[(J + CF_RING - (CF_HALF + CF_G + 1)) % CF_RING];
   const float lag = (s.w + xn) - x20;
   s.w = lag;
-  s.wr[J] = lag;
-  s.xr[J] = xn;
+  s.wr[J % CF_RING] = lag;
+  s.xr[J % CF_RING] = xn;
 
-  const int r = rn - CF_HALF;
-  if (EDGE && r < 0) return;
   bool pass = false;
   if (!EDGE || (r >= CF_HALF && r < p.R - CF_HALF)) {
     float S;
@@ -120,57 +182,93 @@ __device__ __forceinline__ void cfar_step(CfarStep &s, const InT (*__restrict__ 
     if (WITH_THR) {
       const double d = p.tau * (double)S / p.div;
       pass = (double)xc > d;
-      if (col0 + tid < p.B) p.thr[((size_t)f * p.R + r) * p.B + col0 + tid] = (float)d;
+      if (col < p.B) p.thr[((size_t)f * p.R + r) * p.B + col] = (float)d;
     } else {
-      const float u = fmaf(-S, c, xc);       // xc - S*c
-      const float m = fabsf(xc) * 2e-6f;      // >> float32 error of S*c and of the subtraction
-      pass = u > m;
-      if (fabsf(u) <= m) pass = cfar_exact_compare(p.tau, S, p.div, xc);
+      const float u = fmaf(-S, c_lo, fmaf(-S, c_hi, xc));  // xc - S*(tau/div), |error| < 2e-9
+      pass = u > 0.f;
+      amb = amb || (fabsf(u) <= CF_AMBIG);
     }
     pass = pass && (xc > gate);  // gate = -inf when the amplitude gate is off
   }
-  if (BITS) {
-    if (!EDGE || r < p.R) {
-      const unsigned b = __ballot_sync(0xffffffffu, pass && (col0 + tid < p.B));
-      const int w = (col0 >> 5) + (tid >> 5);
-      if ((tid & 31) == 0 && w < p.words_per_row) p.bits[((size_t)f * p.R + r) * p.words_per_row + w] = b;
-    }
-  }
-  if (MASK) {
-    constexpr int orow = (J + CF_RING - CF_HALF) % CF_CH;  // == r % 16
-    // r = 32*body + J - 25  ->  (r / 16) & 1 depends on J only
-    constexpr int ob = ((J + 2 * CF_RING - CF_HALF) / CF_CH) & 1;
-    obuf[ob][orow][tid] = pass ? 1 : 0;
-    if (orow == CF_CH - 1) {
-      fence_proxy_async_smem();
-      if (tid == 0) tma_wait_read<0>();  // the other buffer's store has finished reading
-      named_bar_sync(1, CF_W);
-      if (tid == 0) {
-        tma_store_3d(p.out_map, &obuf[ob][0][0], col0, r - (CF_CH - 1), f);
-        tma_commit();
-      }
-    }
-  }
+  if (MASK) obuf_ob[I][tid] = pass ? 1 : 0;
+  if (BITS) pass_bits |= (pass ? 1u : 0u) << I;
 }
 
+// 16 consecutive output rows r0 .. r0+15 (r0 % 16 == 0).  Needs cells r0+25 .. r0+40: rows 9..15 of
+// TMA box `blk-1` (steps 0..6) and rows 0..8 of box `blk` (steps 7..15), where blk = r0/16 + 2.
 template <typename InT, int ALG, bool WITH_THR, bool MASK, bool BITS, bool EDGE, int Q>
-__device__ __forceinline__ void cfar_block16(CfarStep &s, const InT (*__restrict__ tile)[CF_W],
-                                             uint8_t (*__restrict__ obuf)[CF_CH][CF_W], const CfarParams &p,
-                                             const int rn0, const bool has_chunk, const int tid, const int f,
-                                             const int col0, const float c, const float gate) {
-#define SFE_STEP(I) \
-  cfar_step<InT, ALG, WITH_THR, MASK, BITS, EDGE, Q * CF_CH + I>(s, tile, obuf, p, rn0 + I, has_chunk, tid, f, col0, c, gate);
+__device__ __forceinline__ void cfar_block16(CfarStep &s, InT (*tile)[CF_CH][CF_W], uint8_t (*obuf)[CF_CH][CF_W],
+                                             uint32_t (*obits)[CF_CH][CF_W / 32], uint64_t *full_bar,
+                                             uint64_t *empty_bar, const CfarParams &p, const int blk,
+                                             const int nchunks, const int tid, const int f, const int col0,
+                                             const float c_hi, const float c_lo, const float gate) {
+  const int r0 = (blk - 2) * CF_CH;
+  const int col = col0 + tid;
+  const int cA = blk - 1, cB = blk;
+  const bool hasA = EDGE ? (cA >= 0 && cA < nchunks) : true;
+  const bool hasB = EDGE ? (cB < nchunks) : true;
+  const InT(*tileA)[CF_W] = tile[cA & (CF_NSTAGE - 1)];
+  const InT(*tileB)[CF_W] = tile[cB & (CF_NSTAGE - 1)];
+  constexpr int ob = Q & 1;  // blocks alternate output buffers; Q = blk & 1
+  bool amb = false;
+  uint32_t pass_bits = 0;
+  // All 16 shared-memory reads of the block are issued before any arithmetic so that their latency
+  // is paid once per block, not once per row (a warp issues in order).
+  float xin[CF_CH];
+#pragma unroll
+  for (int i = 0; i < CF_SPLIT; ++i)  // x[r0 + 25 + i] = row 9 + i of box blk-1
+    xin[i] = (!EDGE || hasA) ? cell_to_float(tileA[i + CF_CH - CF_SPLIT][tid]) : 0.f;
+  if (hasB) mbar_wait(&full_bar[cB & (CF_NSTAGE - 1)], (cB / CF_NSTAGE) & 1);
+#pragma unroll
+  for (int i = CF_SPLIT; i < CF_CH; ++i)  // row i - 7 of box blk
+    xin[i] = (!EDGE || hasB) ? cell_to_float(tileB[i - CF_SPLIT][tid]) : 0.f;
+  if (hasA) {  // box blk-1 fully consumed by this warp
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty_bar[cA & (CF_NSTAGE - 1)]);
+  }
+#define SFE_STEP(I)                                                                                          \
+  cfar_step<InT, ALG, WITH_THR, MASK, BITS, EDGE, Q * CF_CH + I>(s, xin[I], obuf[ob], p, r0 + I, tid, f, col, \
+                                                                 c_hi, c_lo, gate, amb, pass_bits);
   SFE_STEP(0) SFE_STEP(1) SFE_STEP(2) SFE_STEP(3) SFE_STEP(4) SFE_STEP(5) SFE_STEP(6) SFE_STEP(7)
   SFE_STEP(8) SFE_STEP(9) SFE_STEP(10) SFE_STEP(11) SFE_STEP(12) SFE_STEP(13) SFE_STEP(14) SFE_STEP(15)
 #undef SFE_STEP
+  if (EDGE && r0 < 0) return;  // priming blocks: no output rows
+  if (!WITH_THR && amb) {
+    uint32_t fixed = 0;
+    cfar_resolve_block<InT>(p, MASK ? obuf[ob] : nullptr, &fixed, f, col, r0, tid);
+    if (BITS) pass_bits = fixed;
+  }
+  if (BITS) {
+    // transpose this thread's 16 row-bits into per-row ballots
+#pragma unroll
+    for (int i = 0; i < CF_CH; ++i) {
+      const unsigned b = __ballot_sync(0xffffffffu, ((pass_bits >> i) & 1u) && col < p.B);
+      if ((tid & 31) == i) obits[ob][i][tid >> 5] = b;
+    }
+  }
+  // hand the 16 finished rows to global memory
+  if (MASK) fence_proxy_async_smem();
+  if (MASK && tid == 0) tma_wait_read<0>();  // the other buffer's TMA store has finished reading it
+  named_bar_sync(1, CF_W);
+  if (MASK && tid == 0) {
+    tma_store_3d(p.out_map, &obuf[ob][0][0], col0, r0, f);
+    tma_commit();
+  }
+  if (BITS && tid < CF_CH * (CF_W / 32)) {
+    const int i = tid / (CF_W / 32), wq = tid % (CF_W / 32);
+    const int w = (col0 >> 5) + wq;
+    if (r0 + i < p.R && w < p.words_per_row)
+      p.bits[((size_t)f * p.R + r0 + i) * p.words_per_row + w] = obits[ob][i][wq];
+  }
 }
 
 template <typename InT, int ALG, bool WITH_THR, bool MASK, bool BITS>
-__global__ void __launch_bounds__(CF_W + 32)
+__global__ void __launch_bounds__(CF_W + 32, 3)
     cfar_ring_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                          CfarParams p) {
   __shared__ __align__(128) InT tile[CF_NSTAGE][CF_CH][CF_W];
   __shared__ __align__(128) uint8_t obuf[2][CF_CH][CF_W];
+  __shared__ uint32_t obits[2][CF_CH][CF_W / 32];
   __shared__ __align__(8) uint64_t full_bar[CF_NSTAGE];
   __shared__ __align__(8) uint64_t empty_bar[CF_NSTAGE];
 
@@ -179,6 +277,7 @@ __global__ void __launch_bounds__(CF_W + 32)
   const int col0 = (blockIdx.x % p.strips) * CF_W;
   const int R = p.R;
   p.out_map = &out_map;
+  const int nchunks = (R + CF_CH - 1) / CF_CH;
 
   if (tid == 0) {
     for (int s = 0; s < CF_NSTAGE; ++s) {
@@ -193,7 +292,6 @@ __global__ void __launch_bounds__(CF_W + 32)
     // ------------------------------------------------------------ producer warp
     if (tid == CF_W) {
       prefetch_tmap(&in_map);
-      const int nchunks = (R + CF_CH - 1) / CF_CH;
       for (int c = 0; c < nchunks; ++c) {
         const int st = c % CF_NSTAGE, it = c / CF_NSTAGE;
         if (it > 0) mbar_wait(&empty_bar[st], (it - 1) & 1);
@@ -209,41 +307,27 @@ __global__ void __launch_bounds__(CF_W + 32)
 #pragma unroll
   for (int i = 0; i < CF_RING; ++i) s.xr[i] = 0.f, s.wr[i] = 0.f;
   s.w = 0.f, s.bad = 0.f, s.mx = 0.f;
-  const float c = p.c;
+  const float c_hi = p.c_hi, c_lo = p.c_lo;
   const float gate = p.gate_on ? p.gate_f : -INFINITY;
 
-  const int r_end = ((R + CF_CH - 1) / CF_CH) * CF_CH;  // rows emitted (TMA store clips rows >= R)
-  const int rn_end = r_end + CF_HALF;                   // newest-row index runs [0, rn_end)
-  const int nblk = (rn_end + CF_CH - 1) / CF_CH;        // 16-row blocks to run
-
-  // block b covers newest rows rn0 = 16 b .. 16 b + 15; its TMA box (if any) sits in stage b % 4 and
-  // completes phase (b / 4) & 1 of that stage's barrier.
+  // block `blk` emits output rows 16*(blk-2) .. +15; blocks 0 and 1 only prime the rings.
+  const int nblk = nchunks + 2;
   for (int b2 = 0; b2 * 2 < nblk; ++b2) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const int b = b2 * 2 + q;
-      if (b < nblk) {
-        const int rn0 = b * CF_CH;
-        const bool has_chunk = rn0 < R;
-        const int st = b % CF_NSTAGE;
-        if (has_chunk) mbar_wait(&full_bar[st], (b / CF_NSTAGE) & 1);
-        const int r0 = rn0 - CF_HALF;
-        const bool interior = (r0 >= CF_HALF) && (r0 + CF_CH - 1 < R - CF_HALF);
+      const int blk = b2 * 2 + q;
+      if (blk < nblk) {
+        const int r0 = (blk - 2) * CF_CH;
+        const bool interior = (r0 >= CF_HALF) && (r0 + CF_CH - 1 < R - CF_HALF);  // implies both boxes exist
+#define SFE_BLOCK(EDGE_, Q_)                                                                                       \
+  cfar_block16<InT, ALG, WITH_THR, MASK, BITS, EDGE_, Q_>(s, tile, obuf, obits, full_bar, empty_bar, p, blk, nchunks, \
+                                                          tid, f, col0, c_hi, c_lo, gate)
         if (interior) {
-          if (q == 0)
-            cfar_block16<InT, ALG, WITH_THR, MASK, BITS, false, 0>(s, tile[st], obuf, p, rn0, true, tid, f, col0, c, gate);
-          else
-            cfar_block16<InT, ALG, WITH_THR, MASK, BITS, false, 1>(s, tile[st], obuf, p, rn0, true, tid, f, col0, c, gate);
+          if (q == 0) SFE_BLOCK(false, 0); else SFE_BLOCK(false, 1);
         } else {
-          if (q == 0)
-            cfar_block16<InT, ALG, WITH_THR, MASK, BITS, true, 0>(s, tile[st], obuf, p, rn0, has_chunk, tid, f, col0, c, gate);
-          else
-            cfar_block16<InT, ALG, WITH_THR, MASK, BITS, true, 1>(s, tile[st], obuf, p, rn0, has_chunk, tid, f, col0, c, gate);
+          if (q == 0) SFE_BLOCK(true, 0); else SFE_BLOCK(true, 1);
         }
-        if (has_chunk) {
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(&empty_bar[st]);
-        }
+#undef SFE_BLOCK
       }
     }
   }
@@ -262,49 +346,15 @@ __global__ void __launch_bounds__(CF_W) cfar_exact_kernel(const InT *__restrict_
   const int col0 = (blockIdx.x % p.strips) * CF_W;
   const int col = col0 + tid;
   const bool live = col < p.B;
-  const int R = p.R, B = p.B, T = p.T, G = p.G;
-  const int half = T + G;
+  const int R = p.R, B = p.B;
+  const int half = p.T + p.G;
   const InT *colp = img + (size_t)f * R * B + (live ? col : 0);
 
   for (int r = 0; r < R; ++r) {
     bool pass = false;
     if (r >= half && r < R - half) {
       double d;
-      if (p.alg == SFE_CFAR_CA) {
-        float acc = 0.f;
-        for (int i = r - half; i <= r + half; ++i)
-          if (abs(i - r) > G) acc = __fadd_rn(acc, cell_to_float(colp[(size_t)i * B]));
-        d = p.tau * (double)acc / p.div;
-      } else if (p.alg == SFE_CFAR_OS) {
-        int n = 0;
-        for (int i = r - half; i <= r + half; ++i)
-          if (abs(i - r) > G) train_smem[(n++) * CF_W + tid] = cell_to_float(colp[(size_t)i * B]);
-        float v = __int_as_float(0x7fc00000);
-        for (int a = 0; a < n; ++a) {  // k-th smallest by rank counting
-          const float va = train_smem[a * CF_W + tid];
-          int less = 0, leq = 0;
-          for (int b = 0; b < n; ++b) {
-            const float vb = train_smem[b * CF_W + tid];
-            less += vb < va;
-            leq += vb <= va;
-          }
-          if (less <= p.k && p.k < leq) {
-            v = va;
-            break;
-          }
-        }
-        d = p.tau * (double)v;
-      } else {
-        float ld = 0.f, lg = 0.f;
-        for (int i = r - half; i < r - G; ++i) ld = __fadd_rn(ld, cell_to_float(colp[(size_t)i * B]));
-        for (int i = r + G + 1; i <= r + half; ++i) lg = __fadd_rn(lg, cell_to_float(colp[(size_t)i * B]));
-        // std::min(lead, lag) / std::max(lead, lag) as written in cfar.cpp:46,69
-        const float S = (p.alg == SFE_CFAR_SOCA) ? (lg < ld ? lg : ld) : (ld < lg ? lg : ld);
-        d = p.tau * (double)S / p.div;
-      }
-      const float xc = cell_to_float(colp[(size_t)r * B]);
-      pass = (double)xc > d;
-      if (p.gate_on) pass = pass && ((double)xc > p.gate_d);
+      pass = cfar_cell_exact<InT>(colp, (size_t)B, r, p, train_smem + tid, CF_W, &d);
       if (p.thr != nullptr && live) p.thr[((size_t)f * R + r) * B + col] = (float)d;
     }
     pass = pass && live;
@@ -340,7 +390,7 @@ static int launch_ring(sfe_ctx *ctx, const CUtensorMap &in_map, const CUtensorMa
 template <typename InT, int ALG>
 static int launch_ring_out(sfe_ctx *ctx, const CUtensorMap &in_map, const CUtensorMap &out_map, const CfarParams &p) {
   const bool m = p.mask != nullptr, b = p.bits != nullptr;
-  if (p.thr != nullptr) {  // the "2" variants: rarely used, one instantiation
+  if (p.thr != nullptr) {  // the "2" variants
     if (m && b) return launch_ring<InT, ALG, true, true, true>(ctx, in_map, out_map, p);
     if (m) return launch_ring<InT, ALG, true, true, false>(ctx, in_map, out_map, p);
     if (b) return launch_ring<InT, ALG, true, false, true>(ctx, in_map, out_map, p);
@@ -400,19 +450,23 @@ int cfar_run(sfe_ctx *ctx, const void *img, int dtype, int F, int R, int B, int 
   p.alg = alg, p.T = T, p.G = G, p.k = k;
   p.tau = tau;
   p.div = alg == SFE_CFAR_CA ? 2.0 * T : (alg == SFE_CFAR_OS ? 1.0 : (double)T);
-  p.c = (float)(tau / p.div);
+  const double c = tau / p.div;
+  p.c_hi = (float)c;
+  p.c_lo = (float)(c - (double)p.c_hi);
   p.gate_on = gate_on != 0;
   p.gate_d = gate;
   p.gate_f = gate_as_float(gate);
+  p.img = img;
   p.mask = mask, p.thr = thr, p.bits = bits;
   p.words_per_row = (B + 31) / 32;
   const size_t es = dtype == SFE_U8 ? 1 : 4;
 
-  // the streaming path's preconditions (shape of the register ring; TMA alignment rules)
+  // the streaming path's preconditions (shape of the register rings; TMA alignment rules; a slope
+  // whose two-float split is accurate)
   bool fast = !force_exact && T == CF_T && G == CF_G && alg != SFE_CFAR_OS && R > 2 * CF_HALF;
   fast = fast && ((uintptr_t)img % 16 == 0) && ((size_t)B * es % 16 == 0);
   if (mask != nullptr) fast = fast && ((uintptr_t)mask % 16 == 0) && (B % 16 == 0);
-  fast = fast && isfinite(tau) && isfinite((double)p.c);
+  fast = fast && isfinite(c) && fabs(c) > 1e-20 && fabs(c) < 1e20;
 
   if (thr != nullptr) SFE_CUDA(cudaMemsetAsync(thr, 0, (size_t)F * R * B * sizeof(float), ctx->stream));
 

@@ -21,7 +21,7 @@ def context(device=None):
     key = (dev, stream)
     ctx = _ctx_cache.get(key)
     if ctx is None:
-        ctx = _ctx_cache[key] = _lib.Context(dev, stream if stream else None)
+        ctx = _ctx_cache[key] = _lib.Context(dev, stream)
     return ctx
 
 
