@@ -93,6 +93,111 @@ SFE_API int sfe_cfar_host(sfe_ctx *ctx, const void *img_host, int dtype, int n_f
                   int train_hs, int guard_hs, int k, double tau, int gate_enable, double gate_threshold,
                   uint8_t *mask_host, float *thr_host);
 
+/* ------------------------------------------------------------------ polar -> Cartesian cloud
+ * Replaces feature_extraction.py:231-238: cv2.remap(mask, map_x, map_y, INTER_LINEAR),
+ * np.nonzero, pixel -> metres.  `sfe_maps` holds, on the device, the per-geometry sampling
+ * table derived from the float32 maps that generate_map_xy builds (feature_extraction.py:134-173;
+ * the maps themselves stay host-side Python).  R x B = polar image (range bins x beams),
+ * rows x cols = Cartesian image, width/height = its extent in metres (self.width, self.height).
+ */
+typedef struct sfe_maps sfe_maps;
+SFE_API int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_host, int rows, int cols, int R,
+                            int B, double width, double height, sfe_maps **out);
+SFE_API void sfe_maps_destroy(sfe_maps *maps);
+
+/* For each of n_frames polar 0/1 masks (bytes [n_frames][R][B], or the bit plane written by
+ * sfe_cfar_dev -- pass exactly one, the other NULL) emit the non-zero Cartesian pixels in row-major
+ * order: ij[f][i] = (row, col) int32 (np.nonzero order), xy[f][i] = (y_forward_m, x_lateral_m)
+ * float32 = float32(points) of feature_extraction.py:238, count[f] = number found.  At most
+ * `capacity` points per frame are written (count still reports the true number). */
+SFE_API int sfe_cart_points_dev(sfe_ctx *ctx, const sfe_maps *maps, const uint8_t *mask_dev, const uint32_t *bits_dev,
+                                int n_frames, int capacity, int32_t *ij_dev, float *xy_dev, int32_t *count_dev);
+/* Host-buffer flavour (byte masks); returns SFE_ERR_CAPACITY if a frame overflowed `capacity`. */
+SFE_API int sfe_cart_points_host(sfe_ctx *ctx, const sfe_maps *maps, const uint8_t *mask_host, int n_frames,
+                                 int capacity, int32_t *ij_host, float *xy_host, int32_t *count_host);
+
+/* ------------------------------------------------------------------ point-cloud filters
+ * Clouds are packed: pts [total][dim] float32 (dim = 2: x,y; remove_outlier also takes 3: x,y,z),
+ * off [n_clouds + 1] int32 offsets (cloud c = rows off[c] .. off[c+1]-1), n_max = largest cloud.
+ * Results are compacted in place of each cloud: out_pts rows off[c] .. off[c]+out_count[c]-1, and
+ * out_idx gives, for every surviving point, its row inside its input cloud.
+ *
+ * sfe_downsample_*      bruce_slam.pcl.downsample (pcl.cpp:128-159): libpointmatcher
+ *                       OctreeGridDataPointsFilter{maxSizeByNode = resolution, samplingMethod = 3}:
+ *                       quadtree on the cloud's bounding square, one medoid per leaf, leaves in
+ *                       depth-first order.  The two-argument overload (points + descriptors,
+ *                       pcl.cpp:143) is served by gathering descriptors with out_idx.
+ * sfe_remove_outlier_*  bruce_slam.pcl.remove_outlier (pcl.cpp:54-74): PCL RadiusOutlierRemoval:
+ *                       keep a point iff at least min_points OTHER points lie within `radius`;
+ *                       input order is preserved.
+ */
+SFE_API int sfe_downsample_dev(sfe_ctx *ctx, const float *pts_dev, const int32_t *off_dev, int n_clouds, int dim,
+                               int n_max, float resolution, float *out_pts_dev, int32_t *out_idx_dev,
+                               int32_t *out_count_dev);
+SFE_API int sfe_remove_outlier_dev(sfe_ctx *ctx, const float *pts_dev, const int32_t *off_dev, int n_clouds, int dim,
+                                   int n_max, double radius, int min_points, float *out_pts_dev,
+                                   int32_t *out_idx_dev, int32_t *out_count_dev);
+/* single-cloud host flavours: n points in, *n_out points out (out buffers hold n entries) */
+SFE_API int sfe_downsample_host(sfe_ctx *ctx, const float *pts_host, int n, int dim, float resolution,
+                                float *out_pts_host, int32_t *out_idx_host, int32_t *n_out);
+SFE_API int sfe_remove_outlier_host(sfe_ctx *ctx, const float *pts_host, int n, int dim, double radius,
+                                    int min_points, float *out_pts_host, int32_t *out_idx_host, int32_t *n_out);
+
+/* ------------------------------------------------------------------ nearest-neighbour match
+ * bruce_slam.pcl.match(ref, in, knn = 1, max_dist) (pcl.cpp:161-174; libpointmatcher KDTreeMatcher):
+ * for every query point the index of the nearest reference point and the SQUARED float32 distance;
+ * no reference point within max_dist -> id -1, dist +inf; ties -> lowest reference index.
+ * Batched over n_pairs (ref cloud p, query cloud p), both packed [total][2] with CSR offsets;
+ * ids / dists are indexed like the query points.  Only knn = 1 (what the reference uses). */
+SFE_API int sfe_match_dev(sfe_ctx *ctx, const float *ref_pts_dev, const int32_t *ref_off_dev, const float *in_pts_dev,
+                          const int32_t *in_off_dev, int n_pairs, int n_ref_max, float max_dist, int32_t *ids_dev,
+                          float *dists_dev);
+SFE_API int sfe_match_host(sfe_ctx *ctx, const float *ref_host, int n_ref, const float *in_host, int n_in,
+                           float max_dist, int32_t *ids_host, float *dists_host);
+
+/* ------------------------------------------------------------------ ICP scan matcher
+ * bruce_slam.pcl.ICP (pcl.cpp:185-213): libpointmatcher PointMatcher<float>::ICP configured by
+ * bruce_slam/config/icp.yaml.  The struct carries what that YAML sets; sfe_icp_params_default()
+ * fills in the shipped values (the host side parses the YAML, see bruce_slam/pcl.py). */
+typedef struct {
+  float matcher_max_dist; /* KDTreeMatcher maxDist                      icp.yaml:9   10.0 */
+  float outlier_max_dist; /* MaxDistOutlierFilter maxDist (<= 0: off)   icp.yaml:13   3.0 */
+  float trim_ratio;       /* TrimmedDistOutlierFilter ratio (< 0: off)  icp.yaml:15   0.8 */
+  int max_iterations;     /* CounterTransformationChecker               icp.yaml:24    40 */
+  float min_diff_rot;     /* DifferentialTransformationChecker          icp.yaml:26  0.01 */
+  float min_diff_trans;   /*                                            icp.yaml:27   0.1 */
+  int smooth_length;      /* (0: differential checker off)              icp.yaml:28     4 */
+  int flags;              /* bit 0: MaxDist filter compares squared distance with maxDist itself */
+} sfe_icp_params;
+SFE_API void sfe_icp_params_default(sfe_icp_params *p);
+
+/* per-problem status (ICP.compute returns the text as its message, pcl.cpp:203-211) */
+enum {
+  SFE_ICP_SUCCESS = 0,      /* "success" */
+  SFE_ICP_NO_OUTLIER = 1,   /* ConvergenceError "no outlier to filter" (no source point has a match) */
+  SFE_ICP_NO_POINT = 2,     /* ConvergenceError "ErrorMnimizer: no point to minimize" */
+  SFE_ICP_NAN_ROT = 3,      /* ConvergenceError "abs rotation norm not a number" */
+  SFE_ICP_NAN_TRANS = 4,    /* ConvergenceError "abs translation norm not a number" */
+  SFE_ICP_NOT_RIGID = 5,    /* TransformationError: the initial guess is not a rigid transform */
+  SFE_ICP_EMPTY_REF = 6     /* the target cloud is empty */
+};
+SFE_API const char *sfe_icp_status_message(int status);
+
+/* Solve n_problems scan matches.  Problem p aligns source cloud src_id[p] to target cloud tgt_id[p]
+ * (ids NULL: cloud p) from the initial guess guess[p] (3x3 row-major float32, as ICP.compute's third
+ * argument); clouds packed [total][2] with CSR offsets, ns_max / nt_max = largest source / target.
+ * Outputs per problem: T (3x3 row-major; = guess when status != 0, like pcl.cpp:207-210), iterations
+ * made, inlier count of the last iteration (pairs with non-zero weight), status. */
+SFE_API int sfe_icp_dev(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts_dev, const int32_t *src_off_dev,
+                        const float *tgt_pts_dev, const int32_t *tgt_off_dev, const int32_t *src_id_dev,
+                        const int32_t *tgt_id_dev, int n_problems, int ns_max, int nt_max, const float *guess_dev,
+                        float *T_dev, int32_t *iters_dev, int32_t *inliers_dev, int32_t *status_dev);
+/* One source / target pair from host memory, n_guesses initial guesses (1 = ICP.compute; >1 = the
+ * loop of SLAM.compute_icp_with_cov, slam.py:346-358, run as one batch). */
+SFE_API int sfe_icp_host(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_host, int ns, const float *tgt_host,
+                         int nt, const float *guess_host, int n_guesses, float *T_host, int32_t *iters_host,
+                         int32_t *inliers_host, int32_t *status_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,3 +95,75 @@ def cfar_reference(alg, img, train_hs, guard_hs, k, tau, want_thr=False):
     if rc:
         raise ValueError("ref_cfar: bad arguments")
     return np.asfortranarray(mask), (np.asfortranarray(thr) if want_thr else None)
+
+
+# ------------------------------------------------------------------ point-cloud helpers / ICP
+class IcpParams(ctypes.Structure):
+    """Mirror of orc_icp_params (oracle/icp_ref.c); defaults = bruce_slam/config/icp.yaml."""
+    _fields_ = [("matcher_max_dist", ctypes.c_float), ("outlier_max_dist", ctypes.c_float),
+                ("trim_ratio", ctypes.c_float), ("max_iterations", ctypes.c_int),
+                ("min_diff_rot", ctypes.c_float), ("min_diff_trans", ctypes.c_float),
+                ("smooth_length", ctypes.c_int), ("flags", ctypes.c_int)]
+
+    def __init__(self, matcher_max_dist=10.0, outlier_max_dist=3.0, trim_ratio=0.8, max_iterations=40,
+                 min_diff_rot=0.01, min_diff_trans=0.1, smooth_length=4, flags=0):
+        super().__init__(matcher_max_dist, outlier_max_dist, trim_ratio, max_iterations, min_diff_rot,
+                         min_diff_trans, smooth_length, flags)
+
+
+ICP_MESSAGES = {0: "success", 1: "no outlier to filter", 2: "ErrorMnimizer: no point to minimize",
+                3: "abs rotation norm not a number", 4: "abs translation norm not a number",
+                5: "RigidTransformation: Error, rotation matrix is not orthogonal.",
+                6: "reference cloud is empty"}
+
+
+def _f32(a, cols=2):
+    a = np.ascontiguousarray(a, np.float32)
+    return a.reshape(-1, cols) if a.size else a.reshape(0, cols)
+
+
+def match(ref, pts, max_dist, brute=False):
+    """pcl.match(ref, pts, 1, max_dist) -> (ids int32 [1,N], squared dists float32 [1,N])."""
+    lib = _load_port()
+    ref, pts = _f32(ref), _f32(pts)
+    ids = np.empty(len(pts), np.int32)
+    d = np.empty(len(pts), np.float32)
+    fn = lib.orc_match_brute if brute else lib.orc_match
+    fn(_p(ref, ctypes.c_float), len(ref), _p(pts, ctypes.c_float), len(pts), ctypes.c_float(max_dist),
+       _p(ids, ctypes.c_int32), _p(d, ctypes.c_float))
+    return ids[None, :], d[None, :]
+
+
+def remove_outlier(pts, radius, min_points):
+    lib = _load_port()
+    pts = np.ascontiguousarray(pts, np.float32)
+    n, dim = pts.shape
+    keep = np.empty(n, np.uint8)
+    lib.orc_remove_outlier(_p(pts, ctypes.c_float), n, dim, ctypes.c_double(radius), int(min_points),
+                           _p(keep, ctypes.c_uint8))
+    return pts[keep.astype(bool)], keep.astype(bool)
+
+
+def downsample(pts, resolution):
+    """pcl.downsample(pts, resolution) -> (kept points float32 in output order, their indices)."""
+    lib = _load_port()
+    pts = _f32(pts)
+    idx = np.empty(len(pts), np.int32)
+    lib.orc_downsample.restype = ctypes.c_int
+    m = lib.orc_downsample(_p(pts, ctypes.c_float), len(pts), ctypes.c_float(resolution), _p(idx, ctypes.c_int32))
+    idx = idx[:m].copy()
+    return pts[idx], idx
+
+
+def icp(src, tgt, guess=None, params=None):
+    """pcl.ICP().compute(src, tgt, guess) -> dict(message, T float32 3x3, iterations, inliers, status)."""
+    lib = _load_port()
+    src, tgt = _f32(src), _f32(tgt)
+    g = np.eye(3, dtype=np.float32) if guess is None else np.ascontiguousarray(guess, np.float32)
+    prm = params or IcpParams()
+    T = np.empty((3, 3), np.float32)
+    it, inl = ctypes.c_int(0), ctypes.c_int(0)
+    st = lib.orc_icp(_p(src, ctypes.c_float), len(src), _p(tgt, ctypes.c_float), len(tgt), _p(g, ctypes.c_float),
+                     ctypes.byref(prm), _p(T, ctypes.c_float), ctypes.byref(it), ctypes.byref(inl))
+    return dict(message=ICP_MESSAGES[st], status=st, T=T if st == 0 else g.copy(), iterations=it.value,
+                inliers=inl.value)

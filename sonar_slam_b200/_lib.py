@@ -47,6 +47,12 @@ def load():
         lib.sfe_cfar_dev.argtypes = cfar_args + [c_void_p]
         lib.sfe_cfar_host.argtypes = cfar_args
         _type_more(lib)
+        lib.sfe_maps_destroy.argtypes = [c_void_p]
+        lib.sfe_maps_destroy.restype = None
+        lib.sfe_icp_status_message.argtypes = [c_int]
+        lib.sfe_icp_status_message.restype = ctypes.c_char_p
+        lib.sfe_icp_params_default.argtypes = [c_void_p]
+        lib.sfe_icp_params_default.restype = None
         _lib = lib
         return lib
 
@@ -59,7 +65,35 @@ def _type_more(lib):
         fn.restype = c_int
 
 
-_EXTRA_SIGNATURES = {}
+_EXTRA_SIGNATURES = {
+    "sfe_maps_create": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
+                        ctypes.POINTER(c_void_p)],
+    "sfe_cart_points_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "sfe_cart_points_host": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "sfe_downsample_dev": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "sfe_remove_outlier_dev": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
+                               c_void_p],
+    "sfe_downsample_host": [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "sfe_remove_outlier_host": [c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p],
+    "sfe_match_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p],
+    "sfe_match_host": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
+    "sfe_icp_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sfe_icp_host": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                     c_void_p, c_void_p],
+}
+
+
+class IcpParams(ctypes.Structure):
+    """sfe_icp_params (include/sonarfe.h); defaults = bruce_slam/config/icp.yaml."""
+    _fields_ = [("matcher_max_dist", c_float), ("outlier_max_dist", c_float), ("trim_ratio", c_float),
+                ("max_iterations", c_int), ("min_diff_rot", c_float), ("min_diff_trans", c_float),
+                ("smooth_length", c_int), ("flags", c_int)]
+
+    def __init__(self, matcher_max_dist=10.0, outlier_max_dist=3.0, trim_ratio=0.8, max_iterations=40,
+                 min_diff_rot=0.01, min_diff_trans=0.1, smooth_length=4, flags=0):
+        super().__init__(matcher_max_dist, outlier_max_dist, trim_ratio, max_iterations, min_diff_rot,
+                         min_diff_trans, smooth_length, flags)
 
 
 def check(rc, what=""):
@@ -111,6 +145,35 @@ def default_context(device=0):
     if ctx is None:
         ctx = _default_ctx[key] = Context(device)
     return ctx
+
+
+class Maps:
+    """Device-resident polar->Cartesian sampling table for one sonar geometry (sfe_maps)."""
+
+    def __init__(self, ctx, map_x, map_y, R, B, width, height):
+        map_x = np.ascontiguousarray(map_x, np.float32)
+        map_y = np.ascontiguousarray(map_y, np.float32)
+        if map_x.shape != map_y.shape or map_x.ndim != 2:
+            raise ValueError("map_x / map_y must be 2-D arrays of the same shape")
+        self.rows, self.cols = map_x.shape
+        self.R, self.B = int(R), int(B)
+        self.width, self.height = float(width), float(height)
+        self.lib = ctx.lib
+        h = c_void_p()
+        check(ctx.lib.sfe_maps_create(ctx.handle, ptr(map_x), ptr(map_y), self.rows, self.cols, self.R, self.B,
+                                      self.width, self.height, ctypes.byref(h)), "sfe_maps_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.sfe_maps_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def ptr(a):

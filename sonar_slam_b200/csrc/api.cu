@@ -181,3 +181,225 @@ int sfe_cfar_host(sfe_ctx *ctx, const void *img_host, int dtype, int n_frames, i
 }
 
 }  // extern "C"
+
+// ============================================================================ clouds / match / ICP
+namespace sfe {
+int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds, int dim, int n_max, float resolution,
+                   float *out_pts, int32_t *out_idx, int32_t *out_count);
+int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds, int dim, int n_max, double radius,
+                       int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count);
+int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const float *tgt_pts,
+            const int *tgt_off, const int *src_id, const int *tgt_id, int P, int ns_max, int nt_max,
+            const float *guess, float *T_out, int *iters, int *inliers, int *status);
+int match_run(sfe_ctx *ctx, const float *ref_pts, const int *ref_off, const float *in_pts, const int *in_off, int P,
+              int nt_max, float max_dist, int32_t *ids, float *dists);
+
+// carve `n` sub-buffers out of one grow-only scratch block (256 B aligned each)
+struct Carver {
+  char *base = nullptr;
+  size_t off = 0;
+  void *take(size_t bytes) {
+    void *p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  }
+};
+}  // namespace sfe
+
+extern "C" {
+
+int sfe_downsample_dev(sfe_ctx *ctx, const float *pts_dev, const int32_t *off_dev, int n_clouds, int dim, int n_max,
+                       float resolution, float *out_pts_dev, int32_t *out_idx_dev, int32_t *out_count_dev) {
+  SFE_REQUIRE(ctx != nullptr, "sfe_downsample_dev: null context");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  return downsample_run(ctx, pts_dev, off_dev, n_clouds, dim, n_max, resolution, out_pts_dev, out_idx_dev,
+                        out_count_dev);
+}
+
+int sfe_remove_outlier_dev(sfe_ctx *ctx, const float *pts_dev, const int32_t *off_dev, int n_clouds, int dim,
+                           int n_max, double radius, int min_points, float *out_pts_dev, int32_t *out_idx_dev,
+                           int32_t *out_count_dev) {
+  SFE_REQUIRE(ctx != nullptr, "sfe_remove_outlier_dev: null context");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  return remove_outlier_run(ctx, pts_dev, off_dev, n_clouds, dim, n_max, radius, min_points, out_pts_dev,
+                            out_idx_dev, out_count_dev);
+}
+
+static int cloud_filter_host(sfe_ctx *ctx, int which, const float *pts_host, int n, int dim, float resolution,
+                             double radius, int min_points, float *out_pts_host, int32_t *out_idx_host,
+                             int32_t *n_out) {
+  SFE_REQUIRE(ctx && n_out, "cloud filter: null context or n_out");
+  SFE_REQUIRE(n >= 0, "cloud filter: negative point count");
+  SFE_REQUIRE(dim == 2 || dim == 3, "cloud filter: points must have 2 or 3 columns (got %d)", dim);
+  *n_out = 0;
+  if (n == 0) return SFE_OK;
+  SFE_REQUIRE(pts_host && out_pts_host && out_idx_host, "cloud filter: null pointer");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  Carver cv;
+  for (int pass = 0; pass < 2; ++pass) {
+    cv.off = 0;
+    float *d_pts = (float *)cv.take(sizeof(float) * (size_t)n * dim);
+    int32_t *d_off = (int32_t *)cv.take(2 * sizeof(int32_t));
+    float *d_out = (float *)cv.take(sizeof(float) * (size_t)n * dim);
+    int32_t *d_idx = (int32_t *)cv.take(sizeof(int32_t) * (size_t)n);
+    int32_t *d_cnt = (int32_t *)cv.take(sizeof(int32_t));
+    if (pass == 0) {
+      int rc = ensure(ctx, ctx->stage_in[1], cv.off);
+      if (rc != SFE_OK) return rc;
+      cv.base = (char *)ctx->stage_in[1].ptr;
+      continue;
+    }
+    const int32_t off[2] = {0, n};
+    SFE_CUDA(cudaMemcpyAsync(d_pts, pts_host, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = which == 0 ? downsample_run(ctx, d_pts, d_off, 1, dim, n, resolution, d_out, d_idx, d_cnt)
+                        : remove_outlier_run(ctx, d_pts, d_off, 1, dim, n, radius, min_points, d_out, d_idx, d_cnt);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaMemcpyAsync(n_out, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(out_pts_host, d_out, sizeof(float) * (size_t)n * dim, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(out_idx_host, d_idx, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SFE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SFE_OK;
+}
+
+int sfe_downsample_host(sfe_ctx *ctx, const float *pts_host, int n, int dim, float resolution, float *out_pts_host,
+                        int32_t *out_idx_host, int32_t *n_out) {
+  return cloud_filter_host(ctx, 0, pts_host, n, dim, resolution, 0.0, 0, out_pts_host, out_idx_host, n_out);
+}
+
+int sfe_remove_outlier_host(sfe_ctx *ctx, const float *pts_host, int n, int dim, double radius, int min_points,
+                            float *out_pts_host, int32_t *out_idx_host, int32_t *n_out) {
+  return cloud_filter_host(ctx, 1, pts_host, n, dim, 0.f, radius, min_points, out_pts_host, out_idx_host, n_out);
+}
+
+int sfe_match_dev(sfe_ctx *ctx, const float *ref_pts_dev, const int32_t *ref_off_dev, const float *in_pts_dev,
+                  const int32_t *in_off_dev, int n_pairs, int n_ref_max, float max_dist, int32_t *ids_dev,
+                  float *dists_dev) {
+  SFE_REQUIRE(ctx != nullptr, "sfe_match_dev: null context");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  return match_run(ctx, ref_pts_dev, ref_off_dev, in_pts_dev, in_off_dev, n_pairs, n_ref_max, max_dist, ids_dev,
+                   dists_dev);
+}
+
+int sfe_match_host(sfe_ctx *ctx, const float *ref_host, int n_ref, const float *in_host, int n_in, float max_dist,
+                   int32_t *ids_host, float *dists_host) {
+  SFE_REQUIRE(ctx != nullptr, "sfe_match_host: null context");
+  SFE_REQUIRE(n_ref >= 0 && n_in >= 0, "sfe_match_host: negative point count");
+  if (n_in == 0) return SFE_OK;
+  SFE_REQUIRE(in_host && ids_host && dists_host && (ref_host || n_ref == 0), "sfe_match_host: null pointer");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  Carver cv;
+  for (int pass = 0; pass < 2; ++pass) {
+    cv.off = 0;
+    float *d_ref = (float *)cv.take(sizeof(float) * 2 * (size_t)(n_ref > 0 ? n_ref : 1));
+    float *d_in = (float *)cv.take(sizeof(float) * 2 * (size_t)n_in);
+    int32_t *d_off = (int32_t *)cv.take(4 * sizeof(int32_t));
+    int32_t *d_ids = (int32_t *)cv.take(sizeof(int32_t) * (size_t)n_in);
+    float *d_d = (float *)cv.take(sizeof(float) * (size_t)n_in);
+    if (pass == 0) {
+      int rc = ensure(ctx, ctx->stage_in[1], cv.off);
+      if (rc != SFE_OK) return rc;
+      cv.base = (char *)ctx->stage_in[1].ptr;
+      continue;
+    }
+    const int32_t off[4] = {0, n_ref, 0, n_in};
+    if (n_ref > 0)
+      SFE_CUDA(cudaMemcpyAsync(d_ref, ref_host, sizeof(float) * 2 * (size_t)n_ref, cudaMemcpyHostToDevice, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(d_in, in_host, sizeof(float) * 2 * (size_t)n_in, cudaMemcpyHostToDevice, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = match_run(ctx, d_ref, d_off, d_in, d_off + 2, 1, n_ref, max_dist, d_ids, d_d);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaMemcpyAsync(ids_host, d_ids, sizeof(int32_t) * (size_t)n_in, cudaMemcpyDeviceToHost, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(dists_host, d_d, sizeof(float) * (size_t)n_in, cudaMemcpyDeviceToHost, ctx->stream));
+    SFE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SFE_OK;
+}
+
+void sfe_icp_params_default(sfe_icp_params *p) {
+  if (!p) return;
+  p->matcher_max_dist = 10.0f;
+  p->outlier_max_dist = 3.0f;
+  p->trim_ratio = 0.8f;
+  p->max_iterations = 40;
+  p->min_diff_rot = 0.01f;
+  p->min_diff_trans = 0.1f;
+  p->smooth_length = 4;
+  p->flags = 0;
+}
+
+const char *sfe_icp_status_message(int status) {
+  switch (status) {
+    case SFE_ICP_SUCCESS: return "success";
+    case SFE_ICP_NO_OUTLIER: return "no outlier to filter";
+    case SFE_ICP_NO_POINT: return "ErrorMnimizer: no point to minimize";
+    case SFE_ICP_NAN_ROT: return "abs rotation norm not a number";
+    case SFE_ICP_NAN_TRANS: return "abs translation norm not a number";
+    case SFE_ICP_NOT_RIGID: return "RigidTransformation: Error, rotation matrix is not orthogonal.";
+    case SFE_ICP_EMPTY_REF: return "reference cloud is empty";
+    default: return "unknown ICP status";
+  }
+}
+
+int sfe_icp_dev(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts_dev, const int32_t *src_off_dev,
+                const float *tgt_pts_dev, const int32_t *tgt_off_dev, const int32_t *src_id_dev,
+                const int32_t *tgt_id_dev, int n_problems, int ns_max, int nt_max, const float *guess_dev, float *T_dev,
+                int32_t *iters_dev, int32_t *inliers_dev, int32_t *status_dev) {
+  SFE_REQUIRE(ctx != nullptr, "sfe_icp_dev: null context");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  return icp_run(ctx, prm, src_pts_dev, src_off_dev, tgt_pts_dev, tgt_off_dev, src_id_dev, tgt_id_dev, n_problems,
+                 ns_max, nt_max, guess_dev, T_dev, iters_dev, inliers_dev, status_dev);
+}
+
+int sfe_icp_host(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_host, int ns, const float *tgt_host, int nt,
+                 const float *guess_host, int n_guesses, float *T_host, int32_t *iters_host, int32_t *inliers_host,
+                 int32_t *status_host) {
+  SFE_REQUIRE(ctx && prm, "sfe_icp_host: null context or parameters");
+  SFE_REQUIRE(ns >= 0 && nt >= 0 && n_guesses >= 0, "sfe_icp_host: negative size");
+  if (n_guesses == 0) return SFE_OK;
+  SFE_REQUIRE(guess_host && T_host && iters_host && inliers_host && status_host, "sfe_icp_host: null pointer");
+  SFE_REQUIRE((src_host || ns == 0) && (tgt_host || nt == 0), "sfe_icp_host: null cloud pointer");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  Carver cv;
+  for (int pass = 0; pass < 2; ++pass) {
+    cv.off = 0;
+    float *d_src = (float *)cv.take(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
+    float *d_tgt = (float *)cv.take(sizeof(float) * 2 * (size_t)(nt > 0 ? nt : 1));
+    int32_t *d_off = (int32_t *)cv.take(4 * sizeof(int32_t));
+    int32_t *d_zero = (int32_t *)cv.take(sizeof(int32_t) * (size_t)n_guesses);
+    float *d_guess = (float *)cv.take(sizeof(float) * 9 * (size_t)n_guesses);
+    float *d_T = (float *)cv.take(sizeof(float) * 9 * (size_t)n_guesses);
+    int32_t *d_res = (int32_t *)cv.take(sizeof(int32_t) * 3 * (size_t)n_guesses);
+    if (pass == 0) {
+      int rc = ensure(ctx, ctx->stage_in[1], cv.off);
+      if (rc != SFE_OK) return rc;
+      cv.base = (char *)ctx->stage_in[1].ptr;
+      continue;
+    }
+    const int32_t off[4] = {0, ns, 0, nt};
+    if (ns > 0)
+      SFE_CUDA(cudaMemcpyAsync(d_src, src_host, sizeof(float) * 2 * (size_t)ns, cudaMemcpyHostToDevice, ctx->stream));
+    if (nt > 0)
+      SFE_CUDA(cudaMemcpyAsync(d_tgt, tgt_host, sizeof(float) * 2 * (size_t)nt, cudaMemcpyHostToDevice, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
+    SFE_CUDA(cudaMemsetAsync(d_zero, 0, sizeof(int32_t) * (size_t)n_guesses, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(d_guess, guess_host, sizeof(float) * 9 * (size_t)n_guesses, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    int rc = icp_run(ctx, prm, d_src, d_off, d_tgt, d_off + 2, d_zero, d_zero, n_guesses, ns, nt, d_guess, d_T, d_res,
+                     d_res + n_guesses, d_res + 2 * n_guesses);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaMemcpyAsync(T_host, d_T, sizeof(float) * 9 * (size_t)n_guesses, cudaMemcpyDeviceToHost, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(iters_host, d_res, sizeof(int32_t) * (size_t)n_guesses, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(inliers_host, d_res + n_guesses, sizeof(int32_t) * (size_t)n_guesses,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    SFE_CUDA(cudaMemcpyAsync(status_host, d_res + 2 * n_guesses, sizeof(int32_t) * (size_t)n_guesses,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    SFE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+// Point-cloud filters (sm_100a): voxel-medoid down-sampling and radius outlier removal.
+//
+// Replace bruce_slam.pcl.downsample and bruce_slam.pcl.remove_outlier
+// (bruce_slam/src/bruce_slam/cpp/pcl.cpp:128-159 and :54-74), i.e. libpointmatcher's
+// OctreeGridDataPointsFilter(maxSizeByNode = resolution, samplingMethod = 3 / medoid) and PCL's
+// RadiusOutlierRemoval, as restated in oracle/cloud_ref.c.  One CTA per cloud, clouds packed
+// [total][dim] with CSR offsets; results are written compacted at the cloud's own offset together
+// with the indices of the surviving points (so descriptor columns can be gathered by the caller,
+// which is how the two-argument downsample overload of pcl.cpp:143 is served).
+//
+// downsample: the quadtree is never materialised.  Splitting always halves the bounding square,
+//   so the leaf a point falls into at the size-limited depth D is found by D comparisons against
+//   centres computed with the same float32 additions the tree would use; the 2-bit child ids along
+//   the path form a key whose ascending order is the tree's depth-first visiting order.  Sorting
+//   (key, index) pairs with an in-CTA bitonic sort therefore groups points by leaf in output order
+//   with members in index order; nodes that the reference stops splitting early because they hold a
+//   single point produce the same groups.  Each group then picks its medoid (float32 sequential sum
+//   of Euclidean distances, first minimum wins).
+// remove_outlier: counts neighbours within the radius on the shared-memory grid of grid.cuh.
+#include "grid.cuh"
+
+namespace sfe {
+
+constexpr int CLOUD_THREADS = 512;
+constexpr int DS_MAX_DEPTH = 15;
+
+struct CloudBatch {
+  const float *pts;  // [total][dim]
+  const int *off;    // [n_clouds + 1]
+  int n_clouds, dim, n_max, n_pad, max_cells;
+  float resolution;  // downsample
+  double radius;     // remove_outlier
+  int min_points;
+  float *out_pts;    // [total][dim]
+  int32_t *out_idx;  // [total] index (within its cloud) of every surviving point
+  int32_t *out_count;  // [n_clouds]
+  unsigned long long *sort_ws;  // global sort buffer when n_pad does not fit shared memory
+  uint16_t *orig_ws;
+  int sort_in_smem;
+};
+
+__global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBatch b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[4 * 32];
+  __shared__ float geo[3];  // cx, cy, radius
+  __shared__ int depth_s;
+  __shared__ int scan[36];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  unsigned long long *keys = b.sort_in_smem ? reinterpret_cast<unsigned long long *>(smem_raw)
+                                            : b.sort_ws + (size_t)blockIdx.x * b.n_pad;
+  float *acc = reinterpret_cast<float *>(smem_raw + (b.sort_in_smem ? sizeof(unsigned long long) * (size_t)b.n_pad : 0));
+
+  for (int cl = blockIdx.x; cl < b.n_clouds; cl += gridDim.x) {
+    const int o = b.off[cl], n = b.off[cl + 1] - o;
+    const float *pts = b.pts + (size_t)o * b.dim;
+    __syncthreads();
+    if (n == 0) {
+      if (tid == 0) b.out_count[cl] = 0;
+      continue;
+    }
+    // ---- bounding square (Octree::build): centre = min + (max-min)*0.5, radius = max extent * 0.5
+    float mn_x = INFINITY, mn_y = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = tid; i < n; i += nthr) {
+      const float x = pts[(size_t)i * b.dim], y = pts[(size_t)i * b.dim + 1];
+      mn_x = fminf(mn_x, x), mxx = fmaxf(mxx, x), mn_y = fminf(mn_y, y), mxy = fmaxf(mxy, y);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn_x = fminf(mn_x, __shfl_xor_sync(0xffffffffu, mn_x, d));
+      mn_y = fminf(mn_y, __shfl_xor_sync(0xffffffffu, mn_y, d));
+      mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+      mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+    }
+    if ((tid & 31) == 0) {
+      red[(tid >> 5) * 4 + 0] = mn_x, red[(tid >> 5) * 4 + 1] = mn_y;
+      red[(tid >> 5) * 4 + 2] = mxx, red[(tid >> 5) * 4 + 3] = mxy;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float a = INFINITY, bb = INFINITY, c = -INFINITY, d = -INFINITY;
+      for (int w = 0; w < (nthr >> 5); ++w) {
+        a = fminf(a, red[w * 4 + 0]), bb = fminf(bb, red[w * 4 + 1]);
+        c = fmaxf(c, red[w * 4 + 2]), d = fmaxf(d, red[w * 4 + 3]);
+      }
+      const float rx = __fsub_rn(c, a), ry = __fsub_rn(d, bb);
+      geo[0] = __fadd_rn(a, __fmul_rn(rx, 0.5f));
+      geo[1] = __fadd_rn(bb, __fmul_rn(ry, 0.5f));
+      float radius = rx;
+      if (radius < ry) radius = ry;
+      radius = __fmul_rn(radius, 0.5f);
+      geo[2] = radius;
+      int D = 0;
+      float r = radius;
+      while (!((double)r * 2.0 <= (double)b.resolution) && D < DS_MAX_DEPTH) r = __fmul_rn(r, 0.5f), ++D;
+      depth_s = D;
+    }
+    __syncthreads();
+    const int D = depth_s;
+    // ---- path key of every point, then sort (key, index)
+    for (int i = tid; i < b.n_pad; i += nthr) {
+      unsigned long long kv = ~0ull;
+      if (i < n) {
+        const float x = pts[(size_t)i * b.dim], y = pts[(size_t)i * b.dim + 1];
+        float cx = geo[0], cy = geo[1], r = geo[2];
+        unsigned key = 0;
+        for (int d = 0; d < D; ++d) {
+          const unsigned id = (x > cx ? 1u : 0u) | (y > cy ? 2u : 0u);
+          key = (key << 2) | id;
+          r = __fmul_rn(r, 0.5f);
+          cx = __fadd_rn(cx, (id & 1u) ? r : -r);
+          cy = __fadd_rn(cy, (id & 2u) ? r : -r);
+        }
+        kv = ((unsigned long long)key << 32) | (unsigned)i;
+      }
+      keys[i] = kv;
+    }
+    __syncthreads();
+    for (int k = 2; k <= b.n_pad; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < b.n_pad; i += nthr) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = keys[i], c = keys[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > c) == up) keys[i] = c, keys[ixj] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- per member: float32 sum of distances to the members of its leaf, in member order
+    for (int a = tid; a < n; a += nthr) {
+      const unsigned key = (unsigned)(keys[a] >> 32);
+      int s = a, e = a + 1;
+      while (s > 0 && (unsigned)(keys[s - 1] >> 32) == key) --s;
+      while (e < n && (unsigned)(keys[e] >> 32) == key) ++e;
+      const int ia = (int)(unsigned)keys[a];
+      const float ax = pts[(size_t)ia * b.dim], ay = pts[(size_t)ia * b.dim + 1];
+      float sum = 0.f;
+      for (int q = s; q < e; ++q) {
+        const int iq = (int)(unsigned)keys[q];
+        sum = __fadd_rn(sum, sqrtf(dist2_rn(ax - pts[(size_t)iq * b.dim], ay - pts[(size_t)iq * b.dim + 1])));
+      }
+      acc[a] = sum;
+    }
+    __syncthreads();
+    // ---- leaf heads pick the medoid; ordered compaction of the leaves
+    int base = 0;
+    for (int c0 = 0; c0 < n; c0 += nthr) {
+      const int a = c0 + tid;
+      bool head = false;
+      int med = 0;
+      if (a < n) {
+        const unsigned key = (unsigned)(keys[a] >> 32);
+        head = (a == 0) || ((unsigned)(keys[a - 1] >> 32) != key);
+        if (head) {
+          float best = 3.402823466e+38f;
+          med = a;
+          for (int q = a; q < n && (unsigned)(keys[q] >> 32) == key; ++q)
+            if (acc[q] < best) best = acc[q], med = q;
+        }
+      }
+      int total;
+      const int rank = block_exclusive_scan(head ? 1 : 0, scan, total);
+      if (head) {
+        const int idx = (int)(unsigned)keys[med];
+        const size_t dst = (size_t)(o + base + rank);
+        for (int d = 0; d < b.dim; ++d) b.out_pts[dst * b.dim + d] = pts[(size_t)idx * b.dim + d];
+        b.out_idx[dst] = idx;
+      }
+      base += total;
+    }
+    if (tid == 0) b.out_count[cl] = base;
+  }
+}
+
+__global__ void __launch_bounds__(CLOUD_THREADS) remove_outlier_kernel(const CloudBatch b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[4 * 32];
+  __shared__ float bbox[4];
+  __shared__ int scan[36];
+  float2 *sorted = reinterpret_cast<float2 *>(smem_raw);
+  uint32_t *cells = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float2) * (size_t)b.n_max);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  uint16_t *orig = b.orig_ws + (size_t)blockIdx.x * b.n_max;
+  const double r2 = b.radius * b.radius;
+  const float rw = (float)(b.radius * (1.0 + 1e-5) + 1e-6);  // search window, slightly widened
+
+  for (int cl = blockIdx.x; cl < b.n_clouds; cl += gridDim.x) {
+    const int o = b.off[cl], n = b.off[cl + 1] - o;
+    const float *pts = b.pts + (size_t)o * b.dim;
+    __syncthreads();
+    if (n == 0) {
+      if (tid == 0) b.out_count[cl] = 0;
+      continue;
+    }
+    float mn_x = INFINITY, mn_y = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = tid; i < n; i += nthr) {
+      const float x = pts[(size_t)i * b.dim], y = pts[(size_t)i * b.dim + 1];
+      mn_x = fminf(mn_x, x), mxx = fmaxf(mxx, x), mn_y = fminf(mn_y, y), mxy = fmaxf(mxy, y);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn_x = fminf(mn_x, __shfl_xor_sync(0xffffffffu, mn_x, d));
+      mn_y = fminf(mn_y, __shfl_xor_sync(0xffffffffu, mn_y, d));
+      mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+      mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+    }
+    if ((tid & 31) == 0) {
+      red[(tid >> 5) * 4 + 0] = mn_x, red[(tid >> 5) * 4 + 1] = mn_y;
+      red[(tid >> 5) * 4 + 2] = mxx, red[(tid >> 5) * 4 + 3] = mxy;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float a = INFINITY, bb = INFINITY, c = -INFINITY, d = -INFINITY;
+      for (int w = 0; w < (nthr >> 5); ++w) {
+        a = fminf(a, red[w * 4 + 0]), bb = fminf(bb, red[w * 4 + 1]);
+        c = fmaxf(c, red[w * 4 + 2]), d = fmaxf(d, red[w * 4 + 3]);
+      }
+      bbox[0] = a, bbox[1] = bb, bbox[2] = c, bbox[3] = d;
+    }
+    __syncthreads();
+    GridView g;
+    grid_geometry(n, bbox[0], bbox[1], bbox[2], bbox[3], (float)(b.radius * 0.5), g, b.max_cells);
+    grid_build(pts, b.dim, n, 0.f, 0.f, g, sorted, cells, orig, scan);
+
+    int base = 0;
+    for (int c0 = 0; c0 < n; c0 += nthr) {
+      const int i = c0 + tid;
+      bool keep = false;
+      if (i < n) {
+        const float qx = pts[(size_t)i * b.dim], qy = pts[(size_t)i * b.dim + 1];
+        const float qz = b.dim == 3 ? pts[(size_t)i * 3 + 2] : 0.f;
+        const int xa = grid_cell_coord(qx - rw, g.ox, g.inv_cell, g.nx), xb = grid_cell_coord(qx + rw, g.ox, g.inv_cell, g.nx);
+        const int ya = grid_cell_coord(qy - rw, g.oy, g.inv_cell, g.ny), yb = grid_cell_coord(qy + rw, g.oy, g.inv_cell, g.ny);
+        int count = 0;
+        for (int y = ya; y <= yb; ++y) {
+          const int s = g.cstart[y * g.nx + xa], e = g.cstart[y * g.nx + xb + 1];
+          for (int q = s; q < e; ++q) {
+            const float2 t = sorted[q];
+            float d2 = __fmul_rn(qx - t.x, qx - t.x);
+            d2 = __fadd_rn(d2, __fmul_rn(qy - t.y, qy - t.y));
+            if (b.dim == 3) {
+              const float dz = qz - pts[(size_t)orig[q] * 3 + 2];
+              d2 = __fadd_rn(d2, __fmul_rn(dz, dz));
+            }
+            count += !(r2 < (double)d2);
+          }
+        }
+        keep = count >= b.min_points + 1;
+      }
+      int total;
+      const int rank = block_exclusive_scan(keep ? 1 : 0, scan, total);
+      if (keep) {
+        const size_t dst = (size_t)(o + base + rank);
+        for (int d = 0; d < b.dim; ++d) b.out_pts[dst * b.dim + d] = pts[(size_t)i * b.dim + d];
+        b.out_idx[dst] = i;
+      }
+      base += total;
+    }
+    if (tid == 0) b.out_count[cl] = base;
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+static int next_pow2(int v) {
+  int p = 2;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds, int dim, int n_max, float resolution,
+                   float *out_pts, int32_t *out_idx, int32_t *out_count) {
+  SFE_REQUIRE(ctx, "downsample: null context");
+  SFE_REQUIRE(n_clouds >= 0 && n_max >= 0, "downsample: negative sizes");
+  SFE_REQUIRE(dim == 2 || dim == 3, "downsample: points must have 2 or 3 columns (got %d)", dim);
+  if (n_clouds == 0) return SFE_OK;
+  SFE_REQUIRE(pts && off && out_pts && out_idx && out_count, "downsample: null pointer");
+  SFE_REQUIRE(dim == 2, "downsample: only 2-column clouds are supported (the reference only passes [x, y])");
+  CloudBatch b{};
+  b.pts = pts, b.off = off, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
+  b.n_pad = next_pow2(b.n_max);
+  b.resolution = resolution;
+  b.out_pts = out_pts, b.out_idx = out_idx, b.out_count = out_count;
+  size_t smem_sort = sizeof(unsigned long long) * (size_t)b.n_pad, smem_acc = sizeof(float) * (size_t)b.n_max + 16;
+  b.sort_in_smem = smem_sort + smem_acc <= (size_t)ctx->max_smem_optin - 4096;
+  size_t smem = (b.sort_in_smem ? smem_sort : 0) + smem_acc;
+  if (smem > (size_t)ctx->max_smem_optin - 4096) {
+    set_error("downsample: clouds of %d points are not supported (shared memory)", n_max);
+    return SFE_ERR_UNSUPPORTED;
+  }
+  SFE_CUDA(cudaFuncSetAttribute(downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, downsample_kernel, CLOUD_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = ctx->sm_count * per_sm;
+  if (grid > n_clouds) grid = n_clouds;
+  if (!b.sort_in_smem) {
+    int rc = ensure(ctx, ctx->scratch[SCR_CLOUD], sizeof(unsigned long long) * (size_t)grid * b.n_pad);
+    if (rc != SFE_OK) return rc;
+    b.sort_ws = (unsigned long long *)ctx->scratch[SCR_CLOUD].ptr;
+  }
+  downsample_kernel<<<grid, CLOUD_THREADS, smem, ctx->stream>>>(b);
+  SFE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SFE_OK;
+}
+
+int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds, int dim, int n_max, double radius,
+                       int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count) {
+  SFE_REQUIRE(ctx, "remove_outlier: null context");
+  SFE_REQUIRE(n_clouds >= 0 && n_max >= 0, "remove_outlier: negative sizes");
+  SFE_REQUIRE(dim == 2 || dim == 3, "remove_outlier: points must have 2 or 3 columns (got %d)", dim);
+  SFE_REQUIRE(radius > 0.0, "remove_outlier: radius must be positive");
+  if (n_clouds == 0) return SFE_OK;
+  SFE_REQUIRE(pts && off && out_pts && out_idx && out_count, "remove_outlier: null pointer");
+  SFE_REQUIRE(n_max <= 65535, "remove_outlier: clouds of more than 65535 points are not supported (got %d)", n_max);
+  CloudBatch b{};
+  b.pts = pts, b.off = off, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
+  b.radius = radius, b.min_points = min_points;
+  b.max_cells = 2 * b.n_max < 256 ? 256 : (2 * b.n_max > GRID_MAX_CELLS ? GRID_MAX_CELLS : 2 * b.n_max);
+  b.out_pts = out_pts, b.out_idx = out_idx, b.out_count = out_count;
+  const size_t smem = sizeof(float2) * (size_t)b.n_max + sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 16;
+  if (smem > (size_t)ctx->max_smem_optin - 4096) {
+    set_error("remove_outlier: clouds of %d points are not supported (shared memory)", n_max);
+    return SFE_ERR_UNSUPPORTED;
+  }
+  SFE_CUDA(cudaFuncSetAttribute(remove_outlier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remove_outlier_kernel, CLOUD_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = ctx->sm_count * per_sm;
+  if (grid > n_clouds) grid = n_clouds;
+  int rc = ensure(ctx, ctx->scratch[SCR_MISC], (size_t)grid * b.n_max * sizeof(uint16_t));
+  if (rc != SFE_OK) return rc;
+  b.orig_ws = (uint16_t *)ctx->scratch[SCR_MISC].ptr;
+  remove_outlier_kernel<<<grid, CLOUD_THREADS, smem, ctx->stream>>>(b);
+  SFE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SFE_OK;
+}
+
+}  // namespace sfe

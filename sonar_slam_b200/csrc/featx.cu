@@ -1,0 +1,311 @@
+// Polar -> Cartesian feature cloud (sm_100a).
+//
+// Replaces the numeric body of FeatureExtraction.callback between the CFAR detector and the
+// point-cloud filters, bruce_slam/src/bruce_slam/feature_extraction.py:231-238:
+//
+//     peaks = cv2.remap(peaks, self.map_x, self.map_y, cv2.INTER_LINEAR)   (:231)
+//     locs  = np.c_[np.nonzero(peaks)]                                      (:232)
+//     x, y  = pixel -> metres ; points = np.column_stack((y, x))            (:235-238)
+//
+// cv2.remap of an 8-bit image with float maps runs in fixed point (OpenCV imgwarp.cpp): the
+// sampling coordinates are quantised to 1/32 px (cvRound = round-half-even), the integer part is
+// saturated to int16, and the four bilinear taps are weighted by 15-bit integers that for 1/32
+// fractions are exactly 32*(32-fx)(32-fy), 32*fx(32-fy), 32*(32-fx)fy, 32*fx*fy; the result is
+// (sum + 2^14) >> 15 with taps outside the image contributing 0.  For a 0/1 mask a Cartesian pixel is
+// therefore non-zero  <=>  sum over set taps of (weight/32) >= 512.  That integer rule is evaluated
+// here per Cartesian pixel from a per-geometry table (8 B/pixel, built once on the host from the same
+// float32 maps the reference builds in generate_map_xy :134-173), against the polar mask held as a
+// bit plane in shared memory; detections are compacted in row-major order (what np.nonzero returns)
+// and converted to metres with the reference's float64 expressions.
+//
+// One CTA handles FPB frames per pass over the table so the table is read once per FPB frames.
+#include <vector>
+
+#include "common.cuh"
+
+struct sfe_maps {
+  int rows, cols;  // Cartesian image
+  int R, B;        // polar image
+  double width, height;
+  void *table;  // device MapEntry[rows*cols]
+  int device;
+};
+
+namespace sfe {
+
+struct __align__(8) MapEntry {
+  int16_t ix, iy;   // top-left tap (saturated like cv::saturate_cast<short>)
+  uint8_t fx, fy;   // 1/32-pixel fractions
+  uint8_t flags;    // bit 0: the pixel can reach weight 512 with in-image taps
+  uint8_t pad;
+};
+
+constexpr int FX_THREADS = 1024;
+
+template <int FPB>
+__global__ void __launch_bounds__(FX_THREADS)
+    cart_points_kernel(const MapEntry *__restrict__ tab, int npix, int cols, int rows, int R, int B, int wpr,
+                       const uint8_t *__restrict__ mask, const uint32_t *__restrict__ bits, int F, int cap,
+                       double width, double height, int32_t *__restrict__ ij, float *__restrict__ xy,
+                       int32_t *__restrict__ count) {
+  extern __shared__ uint32_t sbits[];  // [FPB][R * wpr]
+  __shared__ int wcount[FPB][32];
+  __shared__ int wprefix[FPB][32];
+  __shared__ int wtotal[FPB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f0 = blockIdx.x * FPB;
+  const int words = R * wpr;
+
+  // ---- stage the polar masks of this CTA's frames as bit planes
+#pragma unroll
+  for (int j = 0; j < FPB; ++j) {
+    const int f = f0 + j;
+    uint32_t *sb = sbits + (size_t)j * words;
+    if (f >= F) {
+      for (int w = tid; w < words; w += FX_THREADS) sb[w] = 0;
+    } else if (bits != nullptr) {
+      const uint32_t *src = bits + (size_t)f * words;
+      for (int w = tid; w < words; w += FX_THREADS) sb[w] = src[w];
+    } else {
+      const uint8_t *src = mask + (size_t)f * R * B;
+      const bool vec = (B % 16 == 0) && ((uintptr_t)src % 16 == 0);
+      for (int w = tid; w < words; w += FX_THREADS) {
+        const int r = w / wpr, q = w - r * wpr;
+        const uint8_t *row = src + (size_t)r * B + q * 32;
+        uint32_t word = 0;
+        const int nb = min(32, B - q * 32);
+        if (vec && nb == 32) {
+          const uint4 a = *reinterpret_cast<const uint4 *>(row);
+          const uint4 b = *reinterpret_cast<const uint4 *>(row + 16);
+          const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint32_t nz = v[t];  // four mask bytes (0/1)
+            const uint32_t nib = ((nz & 0xffu) ? 1u : 0u) | ((nz & 0xff00u) ? 2u : 0u) | ((nz & 0xff0000u) ? 4u : 0u) |
+                                 ((nz & 0xff000000u) ? 8u : 0u);
+            word |= nib << (4 * t);
+          }
+        } else {
+          for (int t = 0; t < nb; ++t) word |= (row[t] ? 1u : 0u) << t;
+        }
+        sb[w] = word;
+      }
+    }
+  }
+  __syncthreads();
+
+  int running[FPB];
+#pragma unroll
+  for (int j = 0; j < FPB; ++j) running[j] = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int base = 0; base < npix; base += FX_THREADS) {
+    const int pix = base + tid;
+    bool pass[FPB];
+#pragma unroll
+    for (int j = 0; j < FPB; ++j) pass[j] = false;
+    if (pix < npix) {
+      const MapEntry e = tab[pix];
+      if (e.flags & 1) {
+        const int ix = e.ix, iy = e.iy, fx = e.fx, fy = e.fy;
+        const bool x0 = (unsigned)ix < (unsigned)B, x1 = (unsigned)(ix + 1) < (unsigned)B;
+        const bool y0 = (unsigned)iy < (unsigned)R, y1 = (unsigned)(iy + 1) < (unsigned)R;
+        const int w00 = (x0 && y0) ? (32 - fx) * (32 - fy) : 0, w01 = (x1 && y0) ? fx * (32 - fy) : 0;
+        const int w10 = (x0 && y1) ? (32 - fx) * fy : 0, w11 = (x1 && y1) ? fx * fy : 0;
+        // clamp addresses of dead taps onto a valid word (their weight is 0)
+        const int cx0 = x0 ? ix : 0, cx1 = x1 ? ix + 1 : 0, cy0 = y0 ? iy : 0, cy1 = y1 ? iy + 1 : 0;
+        const int a00 = cy0 * wpr + (cx0 >> 5), a01 = cy0 * wpr + (cx1 >> 5);
+        const int a10 = cy1 * wpr + (cx0 >> 5), a11 = cy1 * wpr + (cx1 >> 5);
+        const int s0 = cx0 & 31, s1 = cx1 & 31;
+#pragma unroll
+        for (int j = 0; j < FPB; ++j) {
+          const uint32_t *sb = sbits + (size_t)j * words;
+          const int sum = w00 * (int)((sb[a00] >> s0) & 1u) + w01 * (int)((sb[a01] >> s1) & 1u) +
+                          w10 * (int)((sb[a10] >> s0) & 1u) + w11 * (int)((sb[a11] >> s1) & 1u);
+          pass[j] = sum >= 512;
+        }
+      }
+    }
+    unsigned bal[FPB];
+    unsigned any = 0;
+#pragma unroll
+    for (int j = 0; j < FPB; ++j) {
+      bal[j] = __ballot_sync(0xffffffffu, pass[j]);
+      any |= bal[j];
+      if (lane == 0) wcount[j][warp] = __popc(bal[j]);
+    }
+    if (__syncthreads_or(any != 0)) {
+      if (warp < FPB) {  // warp j scans the 32 warp counts of frame j
+        const int c = wcount[warp][lane];
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        wprefix[warp][lane] = incl - c;
+        if (lane == 31) wtotal[warp] = incl;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < FPB; ++j) {
+        if (pass[j]) {
+          const int idx = running[j] + wprefix[j][warp] + __popc(bal[j] & lt_mask);
+          if (idx < cap) {
+            const int row = pix / cols, col = pix - row * cols;
+            const size_t o = ((size_t)(f0 + j) * cap + idx) * 2;
+            ij[o] = row;
+            ij[o + 1] = col;
+            // feature_extraction.py:235-237, float64, operation by operation (no contraction)
+            double x = __dsub_rn((double)col, __ddiv_rn((double)cols, 2.0));
+            x = __dmul_rn(__ddiv_rn(x, __ddiv_rn((double)cols, 2.0)), __ddiv_rn(width, 2.0));
+            x = __dmul_rn(-1.0, x);
+            double y = __dmul_rn(-1.0, __ddiv_rn((double)row, (double)rows));
+            y = __dadd_rn(__dmul_rn(y, height), height);
+            xy[o] = (float)y;
+            xy[o + 1] = (float)x;
+          }
+        }
+        running[j] += wtotal[j];
+      }
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int j = 0; j < FPB; ++j)
+      if (f0 + j < F) count[f0 + j] = running[j];
+  }
+}
+
+template <int FPB>
+static int launch_cart(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const uint32_t *bits, int F, int cap,
+                       int32_t *ij, float *xy, int32_t *count) {
+  const int wpr = (m->B + 31) / 32;
+  const size_t smem = (size_t)FPB * m->R * wpr * sizeof(uint32_t);
+  if (smem > (size_t)ctx->max_smem_optin - 1024) return SFE_ERR_UNSUPPORTED;
+  if (smem > 40 * 1024)
+    SFE_CUDA(cudaFuncSetAttribute(cart_points_kernel<FPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (F + FPB - 1) / FPB;
+  cart_points_kernel<FPB><<<grid, FX_THREADS, smem, ctx->stream>>>(
+      (const MapEntry *)m->table, m->rows * m->cols, m->cols, m->rows, m->R, m->B, wpr, mask, bits, F, cap, m->width,
+      m->height, ij, xy, count);
+  SFE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SFE_OK;
+}
+
+int cart_points_run(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const uint32_t *bits, int F, int cap,
+                    int32_t *ij, float *xy, int32_t *count) {
+  SFE_REQUIRE(ctx && m, "cart_points: null context or maps");
+  SFE_REQUIRE(ctx->device == m->device, "cart_points: maps were created on device %d, context is on %d", m->device,
+              ctx->device);
+  SFE_REQUIRE((mask != nullptr) != (bits != nullptr), "cart_points: pass exactly one of mask / bits");
+  SFE_REQUIRE(F >= 0 && cap >= 0, "cart_points: negative frame count or capacity");
+  SFE_REQUIRE(F == 0 || (ij && xy && count), "cart_points: null output pointer");
+  if (F == 0) return SFE_OK;
+  // several frames per CTA amortise the table read once there are enough frames to fill the GPU
+  int rc = SFE_ERR_UNSUPPORTED;
+  if (F >= 4 * ctx->sm_count) rc = launch_cart<4>(ctx, m, mask, bits, F, cap, ij, xy, count);
+  if (rc == SFE_ERR_UNSUPPORTED && F >= 2 * ctx->sm_count) rc = launch_cart<2>(ctx, m, mask, bits, F, cap, ij, xy, count);
+  if (rc == SFE_ERR_UNSUPPORTED) rc = launch_cart<1>(ctx, m, mask, bits, F, cap, ij, xy, count);
+  if (rc == SFE_ERR_UNSUPPORTED)
+    set_error("cart_points: a %d x %d polar bit plane does not fit in shared memory", m->R, m->B);
+  return rc;
+}
+
+}  // namespace sfe
+
+using namespace sfe;
+
+extern "C" {
+
+int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_host, int rows, int cols, int R, int B,
+                    double width, double height, sfe_maps **out) {
+  SFE_REQUIRE(ctx && out, "sfe_maps_create: null context or out pointer");
+  *out = nullptr;
+  SFE_REQUIRE(map_x_host && map_y_host, "sfe_maps_create: null map pointer");
+  SFE_REQUIRE(rows > 0 && cols > 0 && R > 0 && B > 0, "sfe_maps_create: non-positive shape");
+  SFE_REQUIRE((long long)rows * cols < (1ll << 31), "sfe_maps_create: Cartesian image too large");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)rows * cols;
+  std::vector<MapEntry> tab(n);
+  for (size_t p = 0; p < n; ++p) {
+    MapEntry e{};
+    const float mx = map_x_host[p] * 32.0f, my = map_y_host[p] * 32.0f;
+    if (fabsf(mx) < 1.0e9f && fabsf(my) < 1.0e9f) {  // finite and convertible (NaN fails the compare)
+      const int sx = (int)lrintf(mx), sy = (int)lrintf(my);  // cvRound: nearest, ties to even
+      int ix = sx >> 5, iy = sy >> 5;
+      ix = ix < -32768 ? -32768 : (ix > 32767 ? 32767 : ix);
+      iy = iy < -32768 ? -32768 : (iy > 32767 ? 32767 : iy);
+      const int fx = sx & 31, fy = sy & 31;
+      const bool x0 = ix >= 0 && ix < B, x1 = ix + 1 >= 0 && ix + 1 < B;
+      const bool y0 = iy >= 0 && iy < R, y1 = iy + 1 >= 0 && iy + 1 < R;
+      const int reach = (x0 && y0 ? (32 - fx) * (32 - fy) : 0) + (x1 && y0 ? fx * (32 - fy) : 0) +
+                        (x0 && y1 ? (32 - fx) * fy : 0) + (x1 && y1 ? fx * fy : 0);
+      e.ix = (int16_t)ix, e.iy = (int16_t)iy, e.fx = (uint8_t)fx, e.fy = (uint8_t)fy;
+      e.flags = reach >= 512 ? 1 : 0;
+    }
+    tab[p] = e;
+  }
+  sfe_maps *m = new sfe_maps();
+  m->rows = rows, m->cols = cols, m->R = R, m->B = B, m->width = width, m->height = height, m->device = ctx->device;
+  cudaError_t e = cudaMalloc(&m->table, n * sizeof(MapEntry));
+  if (e == cudaSuccess) e = cudaMemcpy(m->table, tab.data(), n * sizeof(MapEntry), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("sfe_maps_create: %s", cudaGetErrorString(e));
+    if (m->table) cudaFree(m->table);
+    delete m;
+    return SFE_ERR_CUDA;
+  }
+  *out = m;
+  return SFE_OK;
+}
+
+void sfe_maps_destroy(sfe_maps *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->table) cudaFree(m->table);
+  delete m;
+}
+
+int sfe_cart_points_dev(sfe_ctx *ctx, const sfe_maps *maps, const uint8_t *mask_dev, const uint32_t *bits_dev,
+                        int n_frames, int capacity, int32_t *ij_dev, float *xy_dev, int32_t *count_dev) {
+  SFE_REQUIRE(ctx != nullptr, "sfe_cart_points_dev: null context");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  return cart_points_run(ctx, maps, mask_dev, bits_dev, n_frames, capacity, ij_dev, xy_dev, count_dev);
+}
+
+int sfe_cart_points_host(sfe_ctx *ctx, const sfe_maps *maps, const uint8_t *mask_host, int n_frames, int capacity,
+                         int32_t *ij_host, float *xy_host, int32_t *count_host) {
+  SFE_REQUIRE(ctx && maps, "sfe_cart_points_host: null context or maps");
+  SFE_REQUIRE(n_frames >= 0 && capacity >= 0, "sfe_cart_points_host: negative frame count or capacity");
+  if (n_frames == 0) return SFE_OK;
+  SFE_REQUIRE(mask_host && ij_host && xy_host && count_host, "sfe_cart_points_host: null pointer");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  const size_t cells = (size_t)n_frames * maps->R * maps->B, slots = (size_t)n_frames * capacity * 2;
+  int rc;
+  if ((rc = ensure(ctx, ctx->stage_in[0], cells)) != SFE_OK) return rc;
+  if ((rc = ensure(ctx, ctx->stage_out[0], slots * sizeof(int32_t) + 16)) != SFE_OK) return rc;
+  if ((rc = ensure(ctx, ctx->stage_out[1], slots * sizeof(float) + 16)) != SFE_OK) return rc;
+  if ((rc = ensure(ctx, ctx->stage_out[2], (size_t)n_frames * sizeof(int32_t))) != SFE_OK) return rc;
+  SFE_CUDA(cudaMemcpyAsync(ctx->stage_in[0].ptr, mask_host, cells, cudaMemcpyHostToDevice, ctx->stream));
+  rc = cart_points_run(ctx, maps, (const uint8_t *)ctx->stage_in[0].ptr, nullptr, n_frames, capacity,
+                       (int32_t *)ctx->stage_out[0].ptr, (float *)ctx->stage_out[1].ptr,
+                       (int32_t *)ctx->stage_out[2].ptr);
+  if (rc != SFE_OK) return rc;
+  SFE_CUDA(cudaMemcpyAsync(count_host, ctx->stage_out[2].ptr, (size_t)n_frames * sizeof(int32_t),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  SFE_CUDA(cudaMemcpyAsync(ij_host, ctx->stage_out[0].ptr, slots * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  SFE_CUDA(cudaMemcpyAsync(xy_host, ctx->stage_out[1].ptr, slots * sizeof(float), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  SFE_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int f = 0; f < n_frames; ++f)
+    if (count_host[f] > capacity) {
+      set_error("sfe_cart_points_host: frame %d has %d points, capacity is %d", f, count_host[f], capacity);
+      return SFE_ERR_CAPACITY;
+    }
+  return SFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,574 @@
+// ICP scan matcher and nearest-neighbour matcher (sm_100a).
+//
+// Replaces bruce_slam.pcl.ICP.compute and bruce_slam.pcl.match
+// (bruce_slam/src/bruce_slam/cpp/pcl.cpp:161-174,185-212), i.e. libpointmatcher's
+// PM::ICP::operator() under bruce_slam/config/icp.yaml: KD-tree NN (knn 1, maxDist 10) ->
+// MaxDist(3.0) x TrimmedDist(0.8) outlier weights -> point-to-point rigid fit ->
+// Counter(40) + Differential(0.01 rad, 0.1 m, smooth 4) checkers, all float32.
+// Algorithm statement and conventions: oracle/icp_ref.c (same steps, same float32 expressions).
+//
+// One CTA solves one (source, target, guess) problem end to end: the target is centred on its
+// mean and counting-sorted into a uniform grid held in shared memory (grid.cuh), the source is
+// moved into the centred frame once, and every iteration runs entirely on chip:
+//   transform + grid NN search per source point  ->  exact k-th smallest distance (4-pass radix
+//   select on the float bits)  ->  0/1 weights  ->  warp-shuffle / shared-memory reductions of the
+//   weighted means and the 2x2 cross-covariance (float32 products, float64 accumulation, fixed
+//   order: deterministic)  ->  closed-form 2-D rotation and translation, T_iter update and the
+//   Counter / Differential checkers on one thread.
+// CTAs are persistent over the problem list (batch of keyframe pairs / of initial guesses).
+#include "grid.cuh"
+
+namespace sfe {
+
+constexpr int ICP_THREADS = 512;
+constexpr int ICP_HIST = 64;  // differential-checker history kept (>= smoothLength + 1)
+
+enum { ICP_OK = 0, ICP_NO_OUTLIER = 1, ICP_NO_POINT = 2, ICP_NAN_ROT = 3, ICP_NAN_TRANS = 4, ICP_NOT_RIGID = 5,
+       ICP_EMPTY_REF = 6 };
+
+struct IcpBatch {
+  const float *src_pts;
+  const int *src_off;
+  const float *tgt_pts;
+  const int *tgt_off;
+  const int *src_id;  // may be null (problem p uses source p)
+  const int *tgt_id;  // may be null
+  const float *guess; // [P][9] row-major 3x3
+  float *T_out;       // [P][9]
+  int *iters, *inliers, *status;
+  int P, ns_max, nt_max, max_cells;
+  sfe_icp_params prm;
+  uint16_t *orig_ws;  // [gridDim.x][nt_max]
+};
+
+__device__ __forceinline__ void mat3_mul_rn(const float *a, const float *b, float *c) {
+  float r[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float acc = __fmul_rn(a[i * 3 + 0], b[0 * 3 + j]);
+      acc = __fadd_rn(acc, __fmul_rn(a[i * 3 + 1], b[1 * 3 + j]));
+      acc = __fadd_rn(acc, __fmul_rn(a[i * 3 + 2], b[2 * 3 + j]));
+      r[i * 3 + j] = acc;
+    }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c[i] = r[i];
+}
+
+__device__ __forceinline__ float2 apply_T(const float *T, float x, float y) {
+  float2 o;
+  o.x = __fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), T[2]);
+  o.y = __fadd_rn(__fadd_rn(__fmul_rn(T[3], x), __fmul_rn(T[4], y)), T[5]);
+  return o;
+}
+
+// Eigen's rotation-matrix -> quaternion conversion for a 2-D rotation embedded in 3x3 (w and z)
+__device__ __forceinline__ void rot_to_quat(const float *T, float &qw, float &qz) {
+  const float m00 = T[0], m01 = T[1], m10 = T[3], m11 = T[4];
+  float t = __fadd_rn(__fadd_rn(m00, m11), 1.0f);
+  if (t > 0.f) {
+    t = sqrtf(__fadd_rn(t, 1.0f));
+    qw = __fmul_rn(0.5f, t);
+    t = __fdiv_rn(0.5f, t);
+    qz = __fmul_rn(__fsub_rn(m10, m01), t);
+  } else {
+    t = sqrtf(__fadd_rn(__fsub_rn(__fsub_rn(1.0f, m00), m11), 1.0f));
+    qz = __fmul_rn(0.5f, t);
+    t = __fdiv_rn(0.5f, t);
+    qw = __fmul_rn(__fsub_rn(m10, m01), t);
+  }
+}
+
+// sum K doubles over the CTA; result valid in out[0..K) for every thread after the call
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double *scratch /* [K][32] smem */, double (&out)[K]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+    if (lane == 0) scratch[k * 32 + warp] = x;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = lane < nwarps ? scratch[k * 32 + lane] : 0.0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+      if (lane == 0) scratch[k * 32] = x;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = scratch[k * 32];
+  __syncthreads();
+}
+
+struct IcpShared {  // small fixed-size part of the shared state
+  float Ti[9];
+  float T0[9];
+  float mean[2];
+  float bbox[4];
+  int iterate, status, count, inliers;
+  int sel_bin, sel_k;
+  int hist[256];
+  int scan[36];
+  double red[8 * 32];
+  float hq_w[ICP_HIST], hq_z[ICP_HIST], ht_x[ICP_HIST], ht_y[ICP_HIST];
+  int hn;
+};
+
+__global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [IcpShared][sorted float2 nt_max][cells u32][reading float2 ns_max][dist f32 ns_max][match u16 ns_max]
+  IcpShared &sh = *reinterpret_cast<IcpShared *>(smem_raw);
+  size_t off = (sizeof(IcpShared) + 15) & ~size_t(15);
+  float2 *sorted = reinterpret_cast<float2 *>(smem_raw + off);
+  off += sizeof(float2) * (size_t)b.nt_max;
+  uint32_t *cells = reinterpret_cast<uint32_t *>(smem_raw + off);
+  off += sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1);
+  off = (off + 7) & ~size_t(7);
+  float2 *reading = reinterpret_cast<float2 *>(smem_raw + off);
+  off += sizeof(float2) * (size_t)b.ns_max;
+  float *dist = reinterpret_cast<float *>(smem_raw + off);
+  off += sizeof(float) * (size_t)b.ns_max;
+  uint16_t *match = reinterpret_cast<uint16_t *>(smem_raw + off);
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  uint16_t *orig = b.orig_ws + (size_t)blockIdx.x * b.nt_max;
+  const sfe_icp_params prm = b.prm;
+  const float max_d2 = __fmul_rn(prm.matcher_max_dist, prm.matcher_max_dist);
+  const float out_d2 = (prm.flags & 1) ? prm.outlier_max_dist : __fmul_rn(prm.outlier_max_dist, prm.outlier_max_dist);
+  const int smooth = min(prm.smooth_length, ICP_HIST - 1);
+
+  for (int p = blockIdx.x; p < b.P; p += gridDim.x) {
+    const int si = b.src_id ? b.src_id[p] : p, ti = b.tgt_id ? b.tgt_id[p] : p;
+    const float *src = b.src_pts + 2 * (size_t)b.src_off[si];
+    const int ns = b.src_off[si + 1] - b.src_off[si];
+    const float *tgt = b.tgt_pts + 2 * (size_t)b.tgt_off[ti];
+    const int nt = b.tgt_off[ti + 1] - b.tgt_off[ti];
+    const float *guess = b.guess + 9 * (size_t)p;
+    __syncthreads();  // previous problem fully retired before shared state is reused
+
+    // ---- admission checks (thread 0), failure leaves T = guess
+    if (tid == 0) {
+      int st = ICP_OK;
+      if (nt <= 0) st = ICP_EMPTY_REF;
+      const float det = __fsub_rn(__fmul_rn(guess[0], guess[4]), __fmul_rn(guess[1], guess[3]));
+      if (st == ICP_OK && (!(fabsf(__fsub_rn(1.0f, det)) <= 0.001f))) st = ICP_NOT_RIGID;
+      sh.status = st;
+      sh.count = 0, sh.inliers = 0;
+    }
+    __syncthreads();
+    if (sh.status != ICP_OK) {
+      if (tid < 9) b.T_out[9 * (size_t)p + tid] = guess[tid];
+      if (tid == 0) b.iters[p] = 0, b.inliers[p] = 0, b.status[p] = sh.status;
+      continue;
+    }
+
+    // ---- 1. mean of the reference, bounding box of the centred reference
+    {
+      double s[2] = {0.0, 0.0}, tot[2];
+      for (int i = tid; i < nt; i += nthr) s[0] += (double)tgt[2 * i], s[1] += (double)tgt[2 * i + 1];
+      block_sum<2>(s, sh.red, tot);
+      const float mx = (float)(tot[0] / (double)nt), my = (float)(tot[1] / (double)nt);
+      float mn_x = INFINITY, mn_y = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+      for (int i = tid; i < nt; i += nthr) {
+        const float x = tgt[2 * i] - mx, y = tgt[2 * i + 1] - my;
+        mn_x = fminf(mn_x, x), mxx = fmaxf(mxx, x), mn_y = fminf(mn_y, y), mxy = fmaxf(mxy, y);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        mn_x = fminf(mn_x, __shfl_xor_sync(0xffffffffu, mn_x, d));
+        mn_y = fminf(mn_y, __shfl_xor_sync(0xffffffffu, mn_y, d));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+      }
+      float *fr = reinterpret_cast<float *>(sh.red);
+      if ((tid & 31) == 0) {
+        fr[(tid >> 5) * 4 + 0] = mn_x, fr[(tid >> 5) * 4 + 1] = mn_y;
+        fr[(tid >> 5) * 4 + 2] = mxx, fr[(tid >> 5) * 4 + 3] = mxy;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float a = INFINITY, bb = INFINITY, c = -INFINITY, d = -INFINITY;
+        for (int w = 0; w < (nthr >> 5); ++w) {
+          a = fminf(a, fr[w * 4 + 0]), bb = fminf(bb, fr[w * 4 + 1]);
+          c = fmaxf(c, fr[w * 4 + 2]), d = fmaxf(d, fr[w * 4 + 3]);
+        }
+        sh.bbox[0] = a, sh.bbox[1] = bb, sh.bbox[2] = c, sh.bbox[3] = d;
+        sh.mean[0] = mx, sh.mean[1] = my;
+      }
+      __syncthreads();
+    }
+    const float mx = sh.mean[0], my = sh.mean[1];
+    GridView g;
+    grid_geometry(nt, sh.bbox[0], sh.bbox[1], sh.bbox[2], sh.bbox[3], 0.05f, g, b.max_cells);
+    grid_build(tgt, 2, nt, mx, my, g, sorted, cells, orig, sh.scan);
+
+    // ---- 2. reading into the centred frame; T_iter = I; checker history
+    if (tid == 0) {
+      const float Tinv[9] = {1.f, 0.f, -mx, 0.f, 1.f, -my, 0.f, 0.f, 1.f};
+      float T0[9];
+      mat3_mul_rn(Tinv, guess, T0);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) sh.T0[i] = T0[i], sh.Ti[i] = (i % 4 == 0) ? 1.f : 0.f;
+      rot_to_quat(sh.Ti, sh.hq_w[0], sh.hq_z[0]);
+      sh.ht_x[0] = 0.f, sh.ht_y[0] = 0.f;
+      sh.hn = 1;
+      sh.iterate = 1;
+    }
+    __syncthreads();
+    for (int i = tid; i < ns; i += nthr) reading[i] = apply_T(sh.T0, src[2 * i], src[2 * i + 1]);
+    __syncthreads();
+
+    // ---- 3. iterations
+    while (true) {
+      float Ti[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Ti[i] = sh.Ti[i];
+      // 3a. match
+      int my_fin = 0;
+      for (int i = tid; i < ns; i += nthr) {
+        const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+        const NNResult r = nn_query(g, q.x, q.y, max_d2);
+        dist[i] = r.d2;
+        match[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
+        my_fin += r.pos >= 0;
+      }
+      // count finite matches (the scan's barriers also publish dist[] / match[])
+      int total_fin;
+      block_exclusive_scan(my_fin, sh.scan, total_fin);
+
+      // 3b. trimmed-distance limit = element floor(float(n)*ratio) of the ascending finite distances
+      float limit = INFINITY;
+      if (prm.trim_ratio >= 0.f) {
+        if (total_fin == 0) {
+          if (tid == 0) sh.status = ICP_NO_OUTLIER;
+          __syncthreads();
+          break;
+        }
+        if (prm.trim_ratio == 1.0f) {
+          float m = 0.f;
+          for (int i = tid; i < ns; i += nthr)
+            if (match[i] != 0xffff) m = fmaxf(m, dist[i]);
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+          float *fr = reinterpret_cast<float *>(sh.red);
+          if ((tid & 31) == 0) fr[tid >> 5] = m;
+          __syncthreads();
+          m = 0.f;
+          for (int w = 0; w < (nthr >> 5); ++w) m = fmaxf(m, fr[w]);
+          limit = m;
+          __syncthreads();
+        } else {
+          int kk = (int)(size_t)__fmul_rn((float)total_fin, prm.trim_ratio);
+          if (kk >= total_fin) kk = total_fin - 1;
+          uint32_t prefix = 0, mask = 0;
+          for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) sh.hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < ns; i += nthr) {
+              if (match[i] == 0xffff) continue;
+              const uint32_t u = __float_as_uint(dist[i]);
+              if ((u & mask) == prefix) atomicAdd(&sh.hist[(u >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            if (tid < 32) {  // lane l owns bins 8l .. 8l+7
+              int c[8], sum = 0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) c[j] = sh.hist[tid * 8 + j], sum += c[j];
+              int incl = sum;
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += t;
+              }
+              int run = incl - sum;
+              if (kk >= run && kk < incl) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (kk >= run && kk < run + c[j]) sh.sel_bin = tid * 8 + j, sh.sel_k = kk - run;
+                  run += c[j];
+                }
+              }
+            }
+            __syncthreads();
+            prefix |= (uint32_t)sh.sel_bin << shift;
+            mask |= 255u << shift;
+            kk = sh.sel_k;
+          }
+          limit = __uint_as_float(prefix);
+        }
+      }
+
+      // 3c. kept pairs: count and sums for the means
+      double s5[5] = {0, 0, 0, 0, 0}, t5[5];
+      for (int i = tid; i < ns; i += nthr) {
+        bool keep = match[i] != 0xffff;
+        if (prm.outlier_max_dist > 0.f) keep = keep && (dist[i] <= out_d2);
+        if (prm.trim_ratio >= 0.f) keep = keep && (dist[i] <= limit);
+        if (!keep) {
+          match[i] = 0xffff;
+          continue;
+        }
+        const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+        const float2 r = sorted[match[i]];
+        s5[0] += 1.0, s5[1] += (double)q.x, s5[2] += (double)q.y, s5[3] += (double)r.x, s5[4] += (double)r.y;
+      }
+      block_sum<5>(s5, sh.red, t5);
+      const int n_keep = (int)t5[0];
+      if (n_keep == 0) {
+        if (tid == 0) sh.status = ICP_NO_POINT;
+        __syncthreads();
+        break;
+      }
+      const float winv = __fdiv_rn(1.0f, (float)n_keep);
+      const float mrx = __fmul_rn((float)t5[1], winv), mry = __fmul_rn((float)t5[2], winv);
+      const float mfx = __fmul_rn((float)t5[3], winv), mfy = __fmul_rn((float)t5[4], winv);
+
+      // 3d. cross-covariance of the centred pairs
+      double s4[4] = {0, 0, 0, 0}, t4[4];
+      for (int i = tid; i < ns; i += nthr) {
+        if (match[i] == 0xffff) continue;
+        const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+        const float2 r = sorted[match[i]];
+        const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
+        const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
+        s4[0] += (double)__fmul_rn(qx, px), s4[1] += (double)__fmul_rn(qx, py);
+        s4[2] += (double)__fmul_rn(qy, px), s4[3] += (double)__fmul_rn(qy, py);
+      }
+      block_sum<4>(s4, sh.red, t4);
+
+      // 3e. rigid fit, T_iter update, checkers (one thread)
+      if (tid == 0) {
+        const float m00 = (float)t4[0], m01 = (float)t4[1], m10 = (float)t4[2], m11 = (float)t4[3];
+        const float a = __fadd_rn(m00, m11), bq = __fsub_rn(m10, m01);
+        const float h = sqrtf(__fadd_rn(__fmul_rn(a, a), __fmul_rn(bq, bq)));
+        float c = 1.f, s = 0.f;
+        if (h > 0.f) c = __fdiv_rn(a, h), s = __fdiv_rn(bq, h);
+        const float tx = __fsub_rn(mfx, __fadd_rn(__fmul_rn(c, mrx), __fmul_rn(-s, mry)));
+        const float ty = __fsub_rn(mfy, __fadd_rn(__fmul_rn(s, mrx), __fmul_rn(c, mry)));
+        const float dT[9] = {c, -s, tx, s, c, ty, 0.f, 0.f, 1.f};
+        float Tn[9];
+        mat3_mul_rn(dT, Ti, Tn);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sh.Ti[i] = Tn[i];
+        sh.inliers = n_keep;
+        const int count = ++sh.count;
+        bool counter_stop = false;
+        if (count >= prm.max_iterations) sh.iterate = 0, counter_stop = true;
+        if (!counter_stop && smooth > 0) {
+          int hn = sh.hn;
+          if (hn == ICP_HIST) {
+            for (int i = 0; i + 1 < ICP_HIST; ++i)
+              sh.hq_w[i] = sh.hq_w[i + 1], sh.hq_z[i] = sh.hq_z[i + 1], sh.ht_x[i] = sh.ht_x[i + 1],
+              sh.ht_y[i] = sh.ht_y[i + 1];
+            hn = ICP_HIST - 1;
+          }
+          rot_to_quat(Tn, sh.hq_w[hn], sh.hq_z[hn]);
+          sh.ht_x[hn] = Tn[2], sh.ht_y[hn] = Tn[5];
+          ++hn;
+          sh.hn = hn;
+          float vr = 0.f, vt = 0.f;
+          if (hn > smooth) {
+            for (int i = hn - 1; i >= hn - smooth; --i) {
+              const float dw = __fadd_rn(__fmul_rn(sh.hq_w[i], sh.hq_w[i - 1]), __fmul_rn(sh.hq_z[i], sh.hq_z[i - 1]));
+              const float dz = __fsub_rn(__fmul_rn(sh.hq_z[i], sh.hq_w[i - 1]), __fmul_rn(sh.hq_w[i], sh.hq_z[i - 1]));
+              vr = __fadd_rn(vr, fabsf(__fmul_rn(2.0f, atan2f(fabsf(dz), fabsf(dw)))));
+              const float ex = __fsub_rn(sh.ht_x[i], sh.ht_x[i - 1]), ey = __fsub_rn(sh.ht_y[i], sh.ht_y[i - 1]);
+              vt = __fadd_rn(vt, fabsf(sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)))));
+            }
+            vr = __fdiv_rn(vr, (float)smooth);
+            vt = __fdiv_rn(vt, (float)smooth);
+            if (vr < prm.min_diff_rot && vt < prm.min_diff_trans) sh.iterate = 0;
+          }
+          if (vr != vr)
+            sh.status = ICP_NAN_ROT;
+          else if (vt != vt)
+            sh.status = ICP_NAN_TRANS;
+        }
+      }
+      __syncthreads();
+      if (sh.status != ICP_OK || !sh.iterate) break;
+    }
+
+    // ---- 4. back to the caller's frame
+    if (tid == 0) {
+      if (sh.status == ICP_OK) {
+        const float Tm[9] = {1.f, 0.f, mx, 0.f, 1.f, my, 0.f, 0.f, 1.f};
+        float tmp[9], out[9], Ti[9], T0[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ti[i] = sh.Ti[i], T0[i] = sh.T0[i];
+        mat3_mul_rn(Tm, Ti, tmp);
+        mat3_mul_rn(tmp, T0, out);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) b.T_out[9 * (size_t)p + i] = out[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) b.T_out[9 * (size_t)p + i] = guess[i];
+      }
+      b.iters[p] = sh.count;
+      b.inliers[p] = sh.inliers;
+      b.status[p] = sh.status;
+    }
+  }
+}
+
+// pcl.match: nearest reference point (within max_dist) of every query point; one CTA per (ref, query) pair
+struct MatchBatch {
+  const float *ref_pts;
+  const int *ref_off;
+  const float *in_pts;
+  const int *in_off;
+  int P, nt_max, max_cells;
+  float max_dist;
+  int32_t *ids;  // [total queries]
+  float *dists;
+  uint16_t *orig_ws;
+};
+
+__global__ void __launch_bounds__(ICP_THREADS) match_kernel(const MatchBatch b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int scan[36];
+  __shared__ float bbox_w[4 * 32];
+  __shared__ float bbox[4];
+  float2 *sorted = reinterpret_cast<float2 *>(smem_raw);
+  uint32_t *cells = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float2) * (size_t)b.nt_max);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  uint16_t *orig = b.orig_ws + (size_t)blockIdx.x * b.nt_max;
+  const float max_d2 = __fmul_rn(b.max_dist, b.max_dist);
+  for (int p = blockIdx.x; p < b.P; p += gridDim.x) {
+    const float *ref = b.ref_pts + 2 * (size_t)b.ref_off[p];
+    const int nt = b.ref_off[p + 1] - b.ref_off[p];
+    const float *in = b.in_pts + 2 * (size_t)b.in_off[p];
+    const int ns = b.in_off[p + 1] - b.in_off[p];
+    int32_t *ids = b.ids + b.in_off[p];
+    float *dists = b.dists + b.in_off[p];
+    __syncthreads();
+    if (nt <= 0) {
+      for (int i = tid; i < ns; i += nthr) ids[i] = -1, dists[i] = INFINITY;
+      continue;
+    }
+    float mn_x = INFINITY, mn_y = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = tid; i < nt; i += nthr) {
+      const float x = ref[2 * i], y = ref[2 * i + 1];
+      mn_x = fminf(mn_x, x), mxx = fmaxf(mxx, x), mn_y = fminf(mn_y, y), mxy = fmaxf(mxy, y);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn_x = fminf(mn_x, __shfl_xor_sync(0xffffffffu, mn_x, d));
+      mn_y = fminf(mn_y, __shfl_xor_sync(0xffffffffu, mn_y, d));
+      mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+      mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+    }
+    if ((tid & 31) == 0) {
+      bbox_w[(tid >> 5) * 4 + 0] = mn_x, bbox_w[(tid >> 5) * 4 + 1] = mn_y;
+      bbox_w[(tid >> 5) * 4 + 2] = mxx, bbox_w[(tid >> 5) * 4 + 3] = mxy;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float a = INFINITY, bb = INFINITY, c = -INFINITY, d = -INFINITY;
+      for (int w = 0; w < (nthr >> 5); ++w) {
+        a = fminf(a, bbox_w[w * 4 + 0]), bb = fminf(bb, bbox_w[w * 4 + 1]);
+        c = fmaxf(c, bbox_w[w * 4 + 2]), d = fmaxf(d, bbox_w[w * 4 + 3]);
+      }
+      bbox[0] = a, bbox[1] = bb, bbox[2] = c, bbox[3] = d;
+    }
+    __syncthreads();
+    GridView g;
+    grid_geometry(nt, bbox[0], bbox[1], bbox[2], bbox[3], 0.05f, g, b.max_cells);
+    grid_build(ref, 2, nt, 0.f, 0.f, g, sorted, cells, orig, scan);
+    for (int i = tid; i < ns; i += nthr) {
+      const NNResult r = nn_query(g, in[2 * i], in[2 * i + 1], max_d2);
+      ids[i] = r.pos >= 0 ? (int32_t)orig[r.pos] : -1;
+      dists[i] = r.d2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+static int pick_max_cells(int nt_max) {
+  int c = 2 * nt_max;
+  if (c < 256) c = 256;
+  if (c > GRID_MAX_CELLS) c = GRID_MAX_CELLS;
+  return c;
+}
+
+int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const float *tgt_pts,
+            const int *tgt_off, const int *src_id, const int *tgt_id, int P, int ns_max, int nt_max,
+            const float *guess, float *T_out, int *iters, int *inliers, int *status) {
+  SFE_REQUIRE(ctx && prm, "icp: null context or parameters");
+  SFE_REQUIRE(P >= 0 && ns_max >= 0 && nt_max >= 0, "icp: negative sizes");
+  if (P == 0) return SFE_OK;
+  SFE_REQUIRE(src_pts && src_off && tgt_pts && tgt_off && guess && T_out && iters && inliers && status,
+              "icp: null pointer");
+  SFE_REQUIRE(nt_max <= 65535 && ns_max <= 65535, "icp: clouds of more than 65535 points are not supported (got %d, %d)",
+              ns_max, nt_max);
+  SFE_REQUIRE(prm->max_iterations >= 1, "icp: maxIterationCount must be >= 1");
+  IcpBatch b{};
+  b.src_pts = src_pts, b.src_off = src_off, b.tgt_pts = tgt_pts, b.tgt_off = tgt_off;
+  b.src_id = src_id, b.tgt_id = tgt_id, b.guess = guess;
+  b.T_out = T_out, b.iters = iters, b.inliers = inliers, b.status = status;
+  b.P = P, b.ns_max = ns_max > 0 ? ns_max : 1, b.nt_max = nt_max > 0 ? nt_max : 1;
+  b.max_cells = pick_max_cells(b.nt_max);
+  b.prm = *prm;
+  size_t smem = ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
+                sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
+                sizeof(float) * (size_t)b.ns_max + sizeof(uint16_t) * (size_t)b.ns_max + 16;
+  if (smem > (size_t)ctx->max_smem_optin) {
+    set_error("icp: source %d + target %d points need %zu B of shared memory per CTA (limit %d)", ns_max, nt_max, smem,
+              ctx->max_smem_optin);
+    return SFE_ERR_UNSUPPORTED;
+  }
+  SFE_CUDA(cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, ICP_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = ctx->sm_count * per_sm;
+  if (grid > P) grid = P;
+  int rc = ensure(ctx, ctx->scratch[SCR_ICP], (size_t)grid * b.nt_max * sizeof(uint16_t));
+  if (rc != SFE_OK) return rc;
+  b.orig_ws = (uint16_t *)ctx->scratch[SCR_ICP].ptr;
+  icp_kernel<<<grid, ICP_THREADS, smem, ctx->stream>>>(b);
+  SFE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SFE_OK;
+}
+
+int match_run(sfe_ctx *ctx, const float *ref_pts, const int *ref_off, const float *in_pts, const int *in_off, int P,
+              int nt_max, float max_dist, int32_t *ids, float *dists) {
+  SFE_REQUIRE(ctx, "match: null context");
+  SFE_REQUIRE(P >= 0 && nt_max >= 0, "match: negative sizes");
+  if (P == 0) return SFE_OK;
+  SFE_REQUIRE(ref_pts && ref_off && in_pts && in_off && ids && dists, "match: null pointer");
+  SFE_REQUIRE(nt_max <= 65535, "match: reference clouds of more than 65535 points are not supported (got %d)", nt_max);
+  MatchBatch b{};
+  b.ref_pts = ref_pts, b.ref_off = ref_off, b.in_pts = in_pts, b.in_off = in_off;
+  b.P = P, b.nt_max = nt_max > 0 ? nt_max : 1, b.max_cells = pick_max_cells(b.nt_max), b.max_dist = max_dist;
+  b.ids = ids, b.dists = dists;
+  const size_t smem = sizeof(float2) * (size_t)b.nt_max + sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 16;
+  if (smem > (size_t)ctx->max_smem_optin) {
+    set_error("match: a %d-point reference needs %zu B of shared memory per CTA (limit %d)", nt_max, smem,
+              ctx->max_smem_optin);
+    return SFE_ERR_UNSUPPORTED;
+  }
+  SFE_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel, ICP_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = ctx->sm_count * per_sm;
+  if (grid > P) grid = P;
+  int rc = ensure(ctx, ctx->scratch[SCR_ICP], (size_t)grid * b.nt_max * sizeof(uint16_t));
+  if (rc != SFE_OK) return rc;
+  b.orig_ws = (uint16_t *)ctx->scratch[SCR_ICP].ptr;
+  match_kernel<<<grid, ICP_THREADS, smem, ctx->stream>>>(b);
+  SFE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SFE_OK;
+}
+
+}  // namespace sfe

@@ -100,8 +100,8 @@ def make_icp_pair(seed, n_source=2000, n_target=20000, extent=60.0, outlier_frac
             T_gt maps source onto target (what ICP should recover from identity).
     """
     rng = np.random.default_rng(seed)
-    n_seg = max(8, int(120 * n_target / 20000))
-    walls = make_walls(rng, n_segments=n_seg, extent=extent)
+    n_seg = max(6, int(48 * n_target / 20000))
+    walls = make_walls(rng, n_segments=n_seg, extent=extent, min_len=15.0, max_len=50.0)
     tgt = grid_thin(sample_walls(rng, walls, 4 * n_target, 0.03), 0.1)
     rng.shuffle(tgt)
     tgt = tgt[:n_target]
