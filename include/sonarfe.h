@@ -59,6 +59,8 @@ SFE_API const char *sfe_last_error(void);
 SFE_API int sfe_ctx_create(int device, void *cuda_stream, int own_stream, sfe_ctx **out);
 SFE_API void sfe_ctx_destroy(sfe_ctx *ctx);
 SFE_API int sfe_sync(sfe_ctx *ctx);
+/* blocking device -> host copy on the context's stream (for callers without a CUDA runtime binding) */
+SFE_API int sfe_copy_to_host(sfe_ctx *ctx, void *dst_host, const void *src_dev, uint64_t bytes);
 /* number of kernels this context has launched so far (bench.py: gpu_launches) */
 SFE_API uint64_t sfe_launch_count(const sfe_ctx *ctx);
 
@@ -179,7 +181,9 @@ enum {
   SFE_ICP_NAN_ROT = 3,      /* ConvergenceError "abs rotation norm not a number" */
   SFE_ICP_NAN_TRANS = 4,    /* ConvergenceError "abs translation norm not a number" */
   SFE_ICP_NOT_RIGID = 5,    /* TransformationError: the initial guess is not a rigid transform */
-  SFE_ICP_EMPTY_REF = 6     /* the target cloud is empty */
+  SFE_ICP_EMPTY_REF = 6,    /* the target cloud is empty */
+  SFE_ICP_SKIPPED = 7,      /* front-end pipeline only: fewer than min_points source/target points (slam.py:654-663) */
+  SFE_ICP_TOO_LARGE = 8     /* front-end pipeline only: a cloud exceeded the configured capacity */
 };
 SFE_API const char *sfe_icp_status_message(int status);
 
@@ -197,6 +201,52 @@ SFE_API int sfe_icp_dev(sfe_ctx *ctx, const sfe_icp_params *prm, const float *sr
 SFE_API int sfe_icp_host(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_host, int ns, const float *tgt_host,
                          int nt, const float *guess_host, int n_guesses, float *T_host, int32_t *iters_host,
                          int32_t *inliers_host, int32_t *status_host);
+
+/* ------------------------------------------------------------------ batched per-keyframe front end
+ * One call for a backlog of frames: FeatureExtraction.callback (feature_extraction.py:196-252)
+ * for every frame, then for every frame i the sequential scan match of SLAM
+ * (slam.py:607-633,718-776): source = cloud i, target = clouds of frames i-window .. i-1 moved into
+ * frame i-1 with the odometry poses and voxel-down-sampled (get_points, slam.py:229-292),
+ * guess = between(pose[i-1], pose[i]), then ICP.  Frame 0 of a batch has no target (status
+ * SFE_ICP_SKIPPED), frames 1 .. window-1 use the frames available.  Pose-graph optimisation is not
+ * part of this library: the SE(2) results feed the caller's (CPU) ISAM2.
+ */
+typedef struct {
+  int R, B;                 /* polar image: range bins x beams (must equal the maps') */
+  int cfar_alg, train_hs, guard_hs, rank; /* feature.yaml CFAR/{alg, Ntc/2, Ngc/2, rank} */
+  double tau;               /* threshold factor of that variant (CFAR.py:71-121, computed by the host) */
+  int gate_enable;          /* feature.yaml filter/threshold: `peaks &= img > threshold` */
+  double gate_threshold;
+  float resolution;         /* feature.yaml filter/resolution (<= 0: no down-sampling) */
+  double outlier_radius;    /* feature.yaml filter/radius */
+  int outlier_min_points;   /* feature.yaml filter/min_points (<= 1: no outlier removal) */
+  int window;               /* slam.yaml ssm/target_frames (3) */
+  float submap_resolution;  /* slam.yaml point_resolution (0.5; <= 0: no down-sampling of the target) */
+  int min_points;           /* slam.yaml ssm/min_points (50) */
+  sfe_icp_params icp;
+  int cap_points;           /* capacity (rows) reserved per frame for its Cartesian cloud */
+  int cap_source, cap_target; /* largest source / target cloud the scan matcher accepts */
+} sfe_frontend_params;
+SFE_API void sfe_frontend_params_default(sfe_frontend_params *p);
+
+typedef struct sfe_frontend sfe_frontend;
+SFE_API int sfe_frontend_create(sfe_ctx *ctx, const sfe_maps *maps, const sfe_frontend_params *params,
+                                int max_frames, sfe_frontend **out);
+SFE_API void sfe_frontend_destroy(sfe_frontend *fe);
+/* frames: uint8 [n_frames][R][B]; poses: float64 [n_frames][3] = odometry (x, y, theta) of every
+ * frame in a common frame, always in HOST memory (24 B per frame).  Device flavour: frames already in
+ * device memory, asynchronous, results stay on the device
+ * (sfe_frontend_results_dev).  Host flavour: copies frames in chunks of `chunk_frames` (<= 0: 256)
+ * overlapped with the kernels, copies the results back and returns when they are there:
+ * T [n][9] (row-major 3x3, source -> previous frame), iterations, inliers, status (SFE_ICP_*),
+ * npoints (size of every frame's filtered cloud; may be NULL). */
+SFE_API int sfe_frontend_run_dev(sfe_frontend *fe, const uint8_t *frames_dev, const double *poses_host, int n_frames);
+SFE_API int sfe_frontend_results_dev(const sfe_frontend *fe, const float **T, const int32_t **iters,
+                                     const int32_t **inliers, const int32_t **status, const float **cloud_xy,
+                                     const int32_t **cloud_count, int32_t *cloud_stride);
+SFE_API int sfe_frontend_run_host(sfe_frontend *fe, const uint8_t *frames_host, const double *poses_host,
+                                  int n_frames, int chunk_frames, float *T_host, int32_t *iters_host,
+                                  int32_t *inliers_host, int32_t *status_host, int32_t *npoints_host);
 
 #ifdef __cplusplus
 }

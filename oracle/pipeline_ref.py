@@ -1,0 +1,66 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle of the batched per-keyframe front end.
+
+Chains the oracle pieces exactly as the reference chains its own calls:
+  per frame    FeatureExtraction.callback, feature_extraction.py:220-249
+               (CFAR -> `&= img > threshold` -> cv2.remap -> nonzero -> metres -> pcl.downsample ->
+               pcl.remove_outlier; float32 where pybind converts)
+  per keyframe SLAM.initialize_sequential_scan_matching / add_sequential_scan_matching,
+               slam.py:626-633,769-771: target = get_points(previous `window` frames, ref = previous
+               frame) = Keyframe.transform_points (float32 `points @ R^T + t`, slam_objects.py:178-198)
+               + concatenate + pcl.downsample; guess = between(pose[i-1], pose[i]); ICP.compute.
+"""
+import math
+
+import numpy as np
+
+from . import featx_ref, oracle as orc
+
+
+def between(a, b):
+    """gtsam Pose2.between(a, b).matrix().astype(float32) for poses (x, y, theta)."""
+    ca, sa = math.cos(a[2]), math.sin(a[2])
+    dx, dy = b[0] - a[0], b[1] - a[1]
+    x, y, th = ca * dx + sa * dy, -sa * dx + ca * dy, b[2] - a[2]
+    c, s = math.cos(th), math.sin(th)
+    return np.array([[c, -s, x], [s, c, y], [0, 0, 1]], np.float64).astype(np.float32)
+
+
+def transform_points(points, T):
+    """Keyframe.transform_points with a float32 T; evaluated element-wise in float32,
+    (x*r00 + y*r01) + tx, so the operation order is defined (numpy's sgemm is not)."""
+    p = points.astype(np.float32)
+    x, y = p[:, 0], p[:, 1]
+    return np.stack([(x * T[0, 0] + y * T[0, 1]) + T[0, 2], (x * T[1, 0] + y * T[1, 1]) + T[1, 2]], 1)
+
+
+def frame_cloud(img, geo, alg="SOCA", train_hs=20, guard_hs=5, rank=10, tau=2.749063720096473, threshold=65,
+                resolution=0.5, radius=1.0, min_points=5):
+    mask = orc.cfar_u8(alg, img, train_hs, guard_hs, rank, tau, threshold)
+    _, pts = featx_ref.cart_points(mask, geo)
+    pts = pts.astype(np.float32)  # pybind: points -> Eigen float matrix
+    if len(pts) and resolution > 0:
+        pts, _ = orc.downsample(pts, resolution)
+    if min_points > 1 and len(pts) > 0:
+        pts, _ = orc.remove_outlier(pts, radius, min_points)
+    return pts
+
+
+def run(frames, poses, geo, window=3, submap_resolution=0.5, min_points=50, icp_params=None, **feat_kw):
+    """Returns (clouds, results); results[i] = dict(status, T, iterations, inliers, n_target)."""
+    prm = icp_params or orc.IcpParams()
+    clouds = [frame_cloud(f, geo, **feat_kw) for f in frames]
+    results = []
+    for i in range(len(frames)):
+        guess = between(poses[i - 1], poses[i]) if i > 0 else np.eye(3, dtype=np.float32)
+        parts = [transform_points(clouds[k], between(poses[i - 1], poses[k])) for k in range(max(0, i - window), i)]
+        tgt = np.concatenate(parts) if parts else np.zeros((0, 2), np.float32)
+        if len(tgt) and submap_resolution > 0:
+            tgt, _ = orc.downsample(tgt, submap_resolution)
+        src = clouds[i]
+        if len(src) < min_points or len(tgt) < min_points:
+            results.append(dict(status=7, T=guess, iterations=0, inliers=0, n_target=len(tgt)))
+            continue
+        r = orc.icp(src, tgt, guess, prm)
+        r["n_target"] = len(tgt)
+        results.append(r)
+    return clouds, results

@@ -53,6 +53,10 @@ def load():
         lib.sfe_icp_status_message.restype = ctypes.c_char_p
         lib.sfe_icp_params_default.argtypes = [c_void_p]
         lib.sfe_icp_params_default.restype = None
+        lib.sfe_frontend_params_default.argtypes = [c_void_p]
+        lib.sfe_frontend_params_default.restype = None
+        lib.sfe_frontend_destroy.argtypes = [c_void_p]
+        lib.sfe_frontend_destroy.restype = None
         _lib = lib
         return lib
 
@@ -79,9 +83,20 @@ _EXTRA_SIGNATURES = {
     "sfe_match_host": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
     "sfe_icp_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                     c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sfe_copy_to_host": [c_void_p, c_void_p, c_void_p, ctypes.c_uint64],
+    "sfe_frontend_create": [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(c_void_p)],
+    "sfe_frontend_run_dev": [c_void_p, c_void_p, c_void_p, c_int],
+    "sfe_frontend_results_dev": [c_void_p] + [ctypes.POINTER(c_void_p)] * 6 + [ctypes.POINTER(ctypes.c_int32)],
+    "sfe_frontend_run_host": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p],
     "sfe_icp_host": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                      c_void_p, c_void_p],
 }
+
+
+class FrontendParams(ctypes.Structure):
+    """sfe_frontend_params (include/sonarfe.h)."""
+    pass
 
 
 class IcpParams(ctypes.Structure):
@@ -94,6 +109,13 @@ class IcpParams(ctypes.Structure):
                  min_diff_rot=0.01, min_diff_trans=0.1, smooth_length=4, flags=0):
         super().__init__(matcher_max_dist, outlier_max_dist, trim_ratio, max_iterations, min_diff_rot,
                          min_diff_trans, smooth_length, flags)
+
+
+FrontendParams._fields_ = [
+    ("R", c_int), ("B", c_int), ("cfar_alg", c_int), ("train_hs", c_int), ("guard_hs", c_int), ("rank", c_int),
+    ("tau", c_double), ("gate_enable", c_int), ("gate_threshold", c_double), ("resolution", c_float),
+    ("outlier_radius", c_double), ("outlier_min_points", c_int), ("window", c_int), ("submap_resolution", c_float),
+    ("min_points", c_int), ("icp", IcpParams), ("cap_points", c_int), ("cap_source", c_int), ("cap_target", c_int)]
 
 
 def check(rc, what=""):
@@ -118,6 +140,12 @@ class Context:
 
     def sync(self):
         check(self.lib.sfe_sync(self.handle), "sfe_sync")
+
+    def to_host(self, dev_ptr, shape, dtype):
+        """Blocking copy of a device buffer (raw address) into a new numpy array."""
+        out = np.empty(shape, dtype)
+        check(self.lib.sfe_copy_to_host(self.handle, ptr(out), c_void_p(int(dev_ptr)), out.nbytes), "sfe_copy_to_host")
+        return out
 
     @property
     def launches(self):

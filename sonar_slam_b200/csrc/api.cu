@@ -143,6 +143,15 @@ int sfe_sync(sfe_ctx *ctx) {
 
 uint64_t sfe_launch_count(const sfe_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int sfe_copy_to_host(sfe_ctx *ctx, void *dst_host, const void *src_dev, uint64_t bytes) {
+  SFE_REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), "sfe_copy_to_host: null argument");
+  if (bytes == 0) return SFE_OK;
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  SFE_CUDA(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SFE_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SFE_OK;
+}
+
 int sfe_cfar_dev(sfe_ctx *ctx, const void *img_dev, int dtype, int n_frames, int R, int B, int alg, int train_hs,
                  int guard_hs, int k, double tau, int gate_enable, double gate_threshold, uint8_t *mask_dev,
                  float *thr_dev, uint32_t *bits_dev) {
@@ -184,13 +193,14 @@ int sfe_cfar_host(sfe_ctx *ctx, const void *img_host, int dtype, int n_frames, i
 
 // ============================================================================ clouds / match / ICP
 namespace sfe {
-int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds, int dim, int n_max, float resolution,
-                   float *out_pts, int32_t *out_idx, int32_t *out_count);
-int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds, int dim, int n_max, double radius,
-                       int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count);
-int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const float *tgt_pts,
-            const int *tgt_off, const int *src_id, const int *tgt_id, int P, int ns_max, int nt_max,
-            const float *guess, float *T_out, int *iters, int *inliers, int *status);
+int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
+                   float resolution, float *out_pts, int32_t *out_idx, int32_t *out_count);
+int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
+                       double radius, int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count);
+int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
+            const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
+            const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,
+            int *inliers, int *status);
 int match_run(sfe_ctx *ctx, const float *ref_pts, const int *ref_off, const float *in_pts, const int *in_off, int P,
               int nt_max, float max_dist, int32_t *ids, float *dists);
 
@@ -212,7 +222,7 @@ int sfe_downsample_dev(sfe_ctx *ctx, const float *pts_dev, const int32_t *off_de
                        float resolution, float *out_pts_dev, int32_t *out_idx_dev, int32_t *out_count_dev) {
   SFE_REQUIRE(ctx != nullptr, "sfe_downsample_dev: null context");
   SFE_CUDA(cudaSetDevice(ctx->device));
-  return downsample_run(ctx, pts_dev, off_dev, n_clouds, dim, n_max, resolution, out_pts_dev, out_idx_dev,
+  return downsample_run(ctx, pts_dev, off_dev, nullptr, n_clouds, dim, n_max, resolution, out_pts_dev, out_idx_dev,
                         out_count_dev);
 }
 
@@ -221,7 +231,7 @@ int sfe_remove_outlier_dev(sfe_ctx *ctx, const float *pts_dev, const int32_t *of
                            int32_t *out_count_dev) {
   SFE_REQUIRE(ctx != nullptr, "sfe_remove_outlier_dev: null context");
   SFE_CUDA(cudaSetDevice(ctx->device));
-  return remove_outlier_run(ctx, pts_dev, off_dev, n_clouds, dim, n_max, radius, min_points, out_pts_dev,
+  return remove_outlier_run(ctx, pts_dev, off_dev, nullptr, n_clouds, dim, n_max, radius, min_points, out_pts_dev,
                             out_idx_dev, out_count_dev);
 }
 
@@ -252,8 +262,9 @@ static int cloud_filter_host(sfe_ctx *ctx, int which, const float *pts_host, int
     const int32_t off[2] = {0, n};
     SFE_CUDA(cudaMemcpyAsync(d_pts, pts_host, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice, ctx->stream));
     SFE_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = which == 0 ? downsample_run(ctx, d_pts, d_off, 1, dim, n, resolution, d_out, d_idx, d_cnt)
-                        : remove_outlier_run(ctx, d_pts, d_off, 1, dim, n, radius, min_points, d_out, d_idx, d_cnt);
+    int rc = which == 0 ? downsample_run(ctx, d_pts, d_off, nullptr, 1, dim, n, resolution, d_out, d_idx, d_cnt)
+                        : remove_outlier_run(ctx, d_pts, d_off, nullptr, 1, dim, n, radius, min_points, d_out, d_idx,
+                                             d_cnt);
     if (rc != SFE_OK) return rc;
     SFE_CUDA(cudaMemcpyAsync(n_out, d_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SFE_CUDA(cudaMemcpyAsync(out_pts_host, d_out, sizeof(float) * (size_t)n * dim, cudaMemcpyDeviceToHost,
@@ -339,6 +350,8 @@ const char *sfe_icp_status_message(int status) {
     case SFE_ICP_NAN_TRANS: return "abs translation norm not a number";
     case SFE_ICP_NOT_RIGID: return "RigidTransformation: Error, rotation matrix is not orthogonal.";
     case SFE_ICP_EMPTY_REF: return "reference cloud is empty";
+    case SFE_ICP_SKIPPED: return "not enough points";
+    case SFE_ICP_TOO_LARGE: return "cloud exceeds the configured capacity";
     default: return "unknown ICP status";
   }
 }
@@ -349,8 +362,8 @@ int sfe_icp_dev(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts_de
                 int32_t *iters_dev, int32_t *inliers_dev, int32_t *status_dev) {
   SFE_REQUIRE(ctx != nullptr, "sfe_icp_dev: null context");
   SFE_CUDA(cudaSetDevice(ctx->device));
-  return icp_run(ctx, prm, src_pts_dev, src_off_dev, tgt_pts_dev, tgt_off_dev, src_id_dev, tgt_id_dev, n_problems,
-                 ns_max, nt_max, guess_dev, T_dev, iters_dev, inliers_dev, status_dev);
+  return icp_run(ctx, prm, src_pts_dev, src_off_dev, nullptr, tgt_pts_dev, tgt_off_dev, nullptr, 0, src_id_dev,
+                 tgt_id_dev, n_problems, ns_max, nt_max, guess_dev, T_dev, iters_dev, inliers_dev, status_dev);
 }
 
 int sfe_icp_host(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_host, int ns, const float *tgt_host, int nt,
@@ -387,8 +400,8 @@ int sfe_icp_host(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_host,
     SFE_CUDA(cudaMemsetAsync(d_zero, 0, sizeof(int32_t) * (size_t)n_guesses, ctx->stream));
     SFE_CUDA(cudaMemcpyAsync(d_guess, guess_host, sizeof(float) * 9 * (size_t)n_guesses, cudaMemcpyHostToDevice,
                              ctx->stream));
-    int rc = icp_run(ctx, prm, d_src, d_off, d_tgt, d_off + 2, d_zero, d_zero, n_guesses, ns, nt, d_guess, d_T, d_res,
-                     d_res + n_guesses, d_res + 2 * n_guesses);
+    int rc = icp_run(ctx, prm, d_src, d_off, nullptr, d_tgt, d_off + 2, nullptr, 0, d_zero, d_zero, n_guesses, ns, nt,
+                     d_guess, d_T, d_res, d_res + n_guesses, d_res + 2 * n_guesses);
     if (rc != SFE_OK) return rc;
     SFE_CUDA(cudaMemcpyAsync(T_host, d_T, sizeof(float) * 9 * (size_t)n_guesses, cudaMemcpyDeviceToHost, ctx->stream));
     SFE_CUDA(cudaMemcpyAsync(iters_host, d_res, sizeof(int32_t) * (size_t)n_guesses, cudaMemcpyDeviceToHost,

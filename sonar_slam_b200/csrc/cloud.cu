@@ -26,7 +26,8 @@ constexpr int DS_MAX_DEPTH = 15;
 
 struct CloudBatch {
   const float *pts;  // [total][dim]
-  const int *off;    // [n_clouds + 1]
+  const int *off;    // [n_clouds + 1] first row of every cloud
+  const int *cnt;    // optional [n_clouds]: rows used (else off[c+1]-off[c]); clamped to n_max
   int n_clouds, dim, n_max, n_pad, max_cells;
   float resolution;  // downsample
   double radius;     // remove_outlier
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
   float *acc = reinterpret_cast<float *>(smem_raw + (b.sort_in_smem ? sizeof(unsigned long long) * (size_t)b.n_pad : 0));
 
   for (int cl = blockIdx.x; cl < b.n_clouds; cl += gridDim.x) {
-    const int o = b.off[cl], n = b.off[cl + 1] - o;
+    const int o = b.off[cl], n = min(b.cnt ? b.cnt[cl] : b.off[cl + 1] - o, b.n_max);
     const float *pts = b.pts + (size_t)o * b.dim;
     __syncthreads();
     if (n == 0) {
@@ -96,8 +97,10 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
     }
     __syncthreads();
     const int D = depth_s;
+    int n_pad = 2;  // bitonic sort size for THIS cloud
+    while (n_pad < n) n_pad <<= 1;
     // ---- path key of every point, then sort (key, index)
-    for (int i = tid; i < b.n_pad; i += nthr) {
+    for (int i = tid; i < n_pad; i += nthr) {
       unsigned long long kv = ~0ull;
       if (i < n) {
         const float x = pts[(size_t)i * b.dim], y = pts[(size_t)i * b.dim + 1];
@@ -115,9 +118,9 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
       keys[i] = kv;
     }
     __syncthreads();
-    for (int k = 2; k <= b.n_pad; k <<= 1) {
+    for (int k = 2; k <= n_pad; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < b.n_pad; i += nthr) {
+        for (int i = tid; i < n_pad; i += nthr) {
           const int ixj = i ^ j;
           if (ixj > i) {
             const unsigned long long a = keys[i], c = keys[ixj];
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(CLOUD_THREADS) remove_outlier_kernel(const Clo
   const float rw = (float)(b.radius * (1.0 + 1e-5) + 1e-6);  // search window, slightly widened
 
   for (int cl = blockIdx.x; cl < b.n_clouds; cl += gridDim.x) {
-    const int o = b.off[cl], n = b.off[cl + 1] - o;
+    const int o = b.off[cl], n = min(b.cnt ? b.cnt[cl] : b.off[cl + 1] - o, b.n_max);
     const float *pts = b.pts + (size_t)o * b.dim;
     __syncthreads();
     if (n == 0) {
@@ -269,7 +272,8 @@ static int next_pow2(int v) {
   return p;
 }
 
-int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds, int dim, int n_max, float resolution,
+int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
+                   float resolution,
                    float *out_pts, int32_t *out_idx, int32_t *out_count) {
   SFE_REQUIRE(ctx, "downsample: null context");
   SFE_REQUIRE(n_clouds >= 0 && n_max >= 0, "downsample: negative sizes");
@@ -278,7 +282,7 @@ int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds,
   SFE_REQUIRE(pts && off && out_pts && out_idx && out_count, "downsample: null pointer");
   SFE_REQUIRE(dim == 2, "downsample: only 2-column clouds are supported (the reference only passes [x, y])");
   CloudBatch b{};
-  b.pts = pts, b.off = off, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
+  b.pts = pts, b.off = off, b.cnt = cnt, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
   b.n_pad = next_pow2(b.n_max);
   b.resolution = resolution;
   b.out_pts = out_pts, b.out_idx = out_idx, b.out_count = out_count;
@@ -306,7 +310,8 @@ int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds,
   return SFE_OK;
 }
 
-int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clouds, int dim, int n_max, double radius,
+int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
+                       double radius,
                        int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count) {
   SFE_REQUIRE(ctx, "remove_outlier: null context");
   SFE_REQUIRE(n_clouds >= 0 && n_max >= 0, "remove_outlier: negative sizes");
@@ -316,7 +321,7 @@ int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, int n_clo
   SFE_REQUIRE(pts && off && out_pts && out_idx && out_count, "remove_outlier: null pointer");
   SFE_REQUIRE(n_max <= 65535, "remove_outlier: clouds of more than 65535 points are not supported (got %d)", n_max);
   CloudBatch b{};
-  b.pts = pts, b.off = off, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
+  b.pts = pts, b.off = off, b.cnt = cnt, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
   b.radius = radius, b.min_points = min_points;
   b.max_cells = 2 * b.n_max < 256 ? 256 : (2 * b.n_max > GRID_MAX_CELLS ? GRID_MAX_CELLS : 2 * b.n_max);
   b.out_pts = out_pts, b.out_idx = out_idx, b.out_count = out_count;

@@ -54,6 +54,14 @@ struct sfe_ctx {
   uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
 };
 
+struct sfe_maps {  // per-geometry polar->Cartesian sampling table (featx.cu)
+  int rows, cols;  // Cartesian image
+  int R, B;        // polar image
+  double width, height;
+  void *table;     // device MapEntry[rows*cols]
+  int device;
+};
+
 namespace sfe {
 enum { SCR_CFAR_FLAGS = 0, SCR_FEATX = 1, SCR_CLOUD = 2, SCR_ICP = 3, SCR_MISC = 4 };
 

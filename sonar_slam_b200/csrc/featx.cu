@@ -23,14 +23,6 @@
 
 #include "common.cuh"
 
-struct sfe_maps {
-  int rows, cols;  // Cartesian image
-  int R, B;        // polar image
-  double width, height;
-  void *table;  // device MapEntry[rows*cols]
-  int device;
-};
-
 namespace sfe {
 
 struct __align__(8) MapEntry {

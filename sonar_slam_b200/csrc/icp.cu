@@ -24,13 +24,16 @@ constexpr int ICP_THREADS = 512;
 constexpr int ICP_HIST = 64;  // differential-checker history kept (>= smoothLength + 1)
 
 enum { ICP_OK = 0, ICP_NO_OUTLIER = 1, ICP_NO_POINT = 2, ICP_NAN_ROT = 3, ICP_NAN_TRANS = 4, ICP_NOT_RIGID = 5,
-       ICP_EMPTY_REF = 6 };
+       ICP_EMPTY_REF = 6, ICP_SKIPPED = 7, ICP_TOO_LARGE = 8 };
 
 struct IcpBatch {
   const float *src_pts;
   const int *src_off;
   const float *tgt_pts;
   const int *tgt_off;
+  const int *src_cnt;  // optional counts (else off[c+1]-off[c])
+  const int *tgt_cnt;
+  int min_points;      // problems whose source or target has fewer points are skipped (ICP_SKIPPED)
   const int *src_id;  // may be null (problem p uses source p)
   const int *tgt_id;  // may be null
   const float *guess; // [P][9] row-major 3x3
@@ -147,16 +150,18 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
   for (int p = blockIdx.x; p < b.P; p += gridDim.x) {
     const int si = b.src_id ? b.src_id[p] : p, ti = b.tgt_id ? b.tgt_id[p] : p;
     const float *src = b.src_pts + 2 * (size_t)b.src_off[si];
-    const int ns = b.src_off[si + 1] - b.src_off[si];
+    const int ns = b.src_cnt ? b.src_cnt[si] : b.src_off[si + 1] - b.src_off[si];
     const float *tgt = b.tgt_pts + 2 * (size_t)b.tgt_off[ti];
-    const int nt = b.tgt_off[ti + 1] - b.tgt_off[ti];
+    const int nt = b.tgt_cnt ? b.tgt_cnt[ti] : b.tgt_off[ti + 1] - b.tgt_off[ti];
     const float *guess = b.guess + 9 * (size_t)p;
     __syncthreads();  // previous problem fully retired before shared state is reused
 
     // ---- admission checks (thread 0), failure leaves T = guess
     if (tid == 0) {
       int st = ICP_OK;
-      if (nt <= 0) st = ICP_EMPTY_REF;
+      if (ns > b.ns_max || nt > b.nt_max) st = ICP_TOO_LARGE;
+      else if (ns < b.min_points || nt < b.min_points) st = ICP_SKIPPED;
+      else if (nt <= 0) st = ICP_EMPTY_REF;
       const float det = __fsub_rn(__fmul_rn(guess[0], guess[4]), __fmul_rn(guess[1], guess[3]));
       if (st == ICP_OK && (!(fabsf(__fsub_rn(1.0f, det)) <= 0.001f))) st = ICP_NOT_RIGID;
       sh.status = st;
@@ -498,9 +503,10 @@ static int pick_max_cells(int nt_max) {
   return c;
 }
 
-int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const float *tgt_pts,
-            const int *tgt_off, const int *src_id, const int *tgt_id, int P, int ns_max, int nt_max,
-            const float *guess, float *T_out, int *iters, int *inliers, int *status) {
+int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
+            const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
+            const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,
+            int *inliers, int *status) {
   SFE_REQUIRE(ctx && prm, "icp: null context or parameters");
   SFE_REQUIRE(P >= 0 && ns_max >= 0 && nt_max >= 0, "icp: negative sizes");
   if (P == 0) return SFE_OK;
@@ -511,6 +517,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   SFE_REQUIRE(prm->max_iterations >= 1, "icp: maxIterationCount must be >= 1");
   IcpBatch b{};
   b.src_pts = src_pts, b.src_off = src_off, b.tgt_pts = tgt_pts, b.tgt_off = tgt_off;
+  b.src_cnt = src_cnt, b.tgt_cnt = tgt_cnt, b.min_points = min_points;
   b.src_id = src_id, b.tgt_id = tgt_id, b.guess = guess;
   b.T_out = T_out, b.iters = iters, b.inliers = inliers, b.status = status;
   b.P = P, b.ns_max = ns_max > 0 ? ns_max : 1, b.nt_max = nt_max > 0 ? nt_max : 1;

@@ -128,3 +128,73 @@ def make_icp_pair(seed, n_source=2000, n_target=20000, extent=60.0, outlier_frac
     Ti = np.linalg.inv(T_gt)
     src = src @ Ti[:2, :2].T + Ti[:2, 2]
     return src.astype(np.float32), tgt_s.astype(np.float32), T_gt
+
+
+# ------------------------------------------------------------------ frames seen from a moving vehicle
+def make_trajectory_frames(n_frames, seed=0, num_ranges=512, num_beams=512, max_range=30.0, bearings=None,
+                           device="cpu", step=0.35, odom_sigma=(0.03, 0.03, 0.004), sigma=18.0):
+    """Synthetic "bag replay": a wall scene insonified from a vehicle moving along a smooth path.
+
+    Returns dict(frames uint8 [n, num_ranges, num_beams] (torch, on `device`),
+                 poses_true float64 [n,3], poses_odom float64 [n,3] (x, y, theta; odometry = truth +
+                 integrated noise), bearings int16 centi-deg).
+    Rendering (torch, runs on CPU or CUDA): wall sample points are moved into the sensor frame,
+    binned to (range bin, beam) and given an echo amplitude; Rayleigh speckle everywhere.
+    """
+    import torch
+
+    rng = np.random.default_rng(seed)
+    if bearings is None:
+        bearings = bearings_oculus(num_beams)
+    b_rad = np.deg2rad(bearings.astype(np.float64) / 100.0)
+    walls = make_walls(rng, n_segments=30, extent=90.0, min_len=15.0, max_len=45.0)
+    seg_len = np.hypot(walls[:, 2] - walls[:, 0], walls[:, 3] - walls[:, 1])
+    pts, amp = [], []
+    for w, L in zip(walls, seg_len):
+        m = int(L / 0.04)
+        t = (np.arange(m) + 0.5) / m
+        pts.append(w[:2] + (w[2:] - w[:2]) * t[:, None])
+        amp.append(np.full(m, rng.uniform(110.0, 200.0)))
+    pts, amp = np.concatenate(pts), np.concatenate(amp)
+    # smooth path inside the scene
+    th = 0.4 + np.cumsum(rng.normal(0, 0.01, n_frames)) + 0.15 * np.sin(np.arange(n_frames) / 40.0)
+    xy = np.c_[np.cumsum(step * np.cos(th)), np.cumsum(step * np.sin(th))]
+    xy = 45.0 + (xy - xy.mean(0)) * min(1.0, 35.0 / max(1e-9, np.abs(xy - xy.mean(0)).max()))
+    poses_true = np.c_[xy, th]
+    # odometry: per-step noise in the body frame, integrated
+    odom = np.zeros_like(poses_true)
+    odom[0] = poses_true[0]
+    for i in range(1, n_frames):
+        a, b = poses_true[i - 1], poses_true[i]
+        c, s = np.cos(a[2]), np.sin(a[2])
+        d = np.array([c * (b[0] - a[0]) + s * (b[1] - a[1]), -s * (b[0] - a[0]) + c * (b[1] - a[1]), b[2] - a[2]])
+        d += rng.normal(0, odom_sigma)
+        c, s = np.cos(odom[i - 1, 2]), np.sin(odom[i - 1, 2])
+        odom[i] = [odom[i - 1, 0] + c * d[0] - s * d[1], odom[i - 1, 1] + s * d[0] + c * d[1], odom[i - 1, 2] + d[2]]
+
+    dev = torch.device(device)
+    P = torch.from_numpy(pts).to(dev)
+    A = torch.from_numpy(amp).to(dev, torch.float32)
+    bt = torch.from_numpy(b_rad).to(dev)
+    res = max_range / num_ranges
+    gen = torch.Generator(device=dev).manual_seed(int(seed))
+    frames = torch.empty((n_frames, num_ranges, num_beams), dtype=torch.uint8, device=dev)
+    chunk = 32 if dev.type == "cuda" else 8
+    for f0 in range(0, n_frames, chunk):
+        n = min(chunk, n_frames - f0)
+        pose = torch.from_numpy(poses_true[f0:f0 + n]).to(dev)
+        c, s = torch.cos(pose[:, 2])[:, None], torch.sin(pose[:, 2])[:, None]
+        dx, dy = P[None, :, 0] - pose[:, 0:1], P[None, :, 1] - pose[:, 1:2]
+        xs, ys = c * dx + s * dy, -s * dx + c * dy
+        r, b = torch.hypot(xs, ys), torch.atan2(ys, xs)
+        rb = torch.floor(r / res).long()
+        bb = torch.searchsorted(bt, b.contiguous()).clamp_(0, num_beams - 1)
+        ok = (rb >= 1) & (rb < num_ranges - 2) & (b > bt[0]) & (b < bt[-1])
+        u = torch.rand((n, num_ranges, num_beams), device=dev, generator=gen).clamp_min_(1e-7)
+        img = sigma * torch.sqrt(-2.0 * torch.log(u))
+        fi = torch.arange(n, device=dev)[:, None].expand_as(rb)
+        for dr in (0, 1):  # echoes are two range bins thick
+            flat = (fi * num_ranges + rb + dr) * num_beams + bb
+            img.view(-1).scatter_reduce_(0, flat[ok], A[None, :].expand_as(rb)[ok] + sigma, "amax")
+        frames[f0:f0 + n] = torch.clamp(torch.round(img), 0, 255).to(torch.uint8)
+    return dict(frames=frames, poses_true=poses_true, poses_odom=odom, bearings=bearings)
