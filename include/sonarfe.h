@@ -244,6 +244,13 @@ SFE_API int sfe_frontend_run_dev(sfe_frontend *fe, const uint8_t *frames_dev, co
 SFE_API int sfe_frontend_results_dev(const sfe_frontend *fe, const float **T, const int32_t **iters,
                                      const int32_t **inliers, const int32_t **status, const float **cloud_xy,
                                      const int32_t **cloud_count, int32_t *cloud_stride);
+/* Optional per-stage device timing (CUDA events on the launch stream around every stage's kernels).
+ * get_timing synchronises, adds the intervals recorded since the last call to running totals and
+ * returns the totals: stage_ms[SFE_FE_STAGES], stage_calls[SFE_FE_STAGES] (may be NULL). */
+enum { SFE_FE_CFAR = 0, SFE_FE_CART = 1, SFE_FE_DOWNSAMPLE = 2, SFE_FE_OUTLIER = 3, SFE_FE_SUBMAP = 4,
+       SFE_FE_ICP = 5, SFE_FE_STAGES = 6 };
+SFE_API int sfe_frontend_set_timing(sfe_frontend *fe, int enable);
+SFE_API int sfe_frontend_get_timing(sfe_frontend *fe, double *stage_ms, int64_t *stage_calls);
 SFE_API int sfe_frontend_run_host(sfe_frontend *fe, const uint8_t *frames_host, const double *poses_host,
                                   int n_frames, int chunk_frames, float *T_host, int32_t *iters_host,
                                   int32_t *inliers_host, int32_t *status_host, int32_t *npoints_host);

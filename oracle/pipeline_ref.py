@@ -34,8 +34,13 @@ def transform_points(points, T):
 
 
 def frame_cloud(img, geo, alg="SOCA", train_hs=20, guard_hs=5, rank=10, tau=2.749063720096473, threshold=65,
-                resolution=0.5, radius=1.0, min_points=5):
-    mask = orc.cfar_u8(alg, img, train_hs, guard_hs, rank, tau, threshold)
+                resolution=0.5, radius=1.0, min_points=5, use_reference=False):
+    if use_reference and orc.have_reference():  # the unmodified reference cfar.cpp (oracle/_ref)
+        mask, _ = orc.cfar_reference(alg, img, train_hs, guard_hs, rank, tau)
+        mask = np.ascontiguousarray(mask)
+        mask &= img > threshold
+    else:
+        mask = orc.cfar_u8(alg, img, train_hs, guard_hs, rank, tau, threshold)
     _, pts = featx_ref.cart_points(mask, geo)
     pts = pts.astype(np.float32)  # pybind: points -> Eigen float matrix
     if len(pts) and resolution > 0:

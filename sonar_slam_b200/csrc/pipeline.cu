@@ -13,6 +13,8 @@
 // Device layout: every per-frame cloud lives at a fixed stride (`cap_points` rows) with a count
 // array, so all stages run without packing or host round trips; the host flavour overlaps the
 // host->device copy of frame chunk k+1 with the kernels of chunk k on two streams.
+#include <vector>
+
 #include "common.cuh"
 
 namespace sfe {
@@ -104,8 +106,30 @@ struct sfe_frontend {
   int32_t *iters, *inliers, *status;
   cudaStream_t copy_stream;
   cudaEvent_t ev_copy[2], ev_done;
-  void *pinned_out;
+  // optional per-stage timing (CUDA events on the launch stream)
+  int timing;
+  std::vector<cudaEvent_t> *tev;    // pool
+  std::vector<int> *tstage;         // stage id of interval [2k, 2k+1]
+  size_t tused;
+  double stage_ms[SFE_FE_STAGES];
+  long long stage_launches[SFE_FE_STAGES];
 };
+
+static void fe_tic(sfe_frontend *fe, int stage) {
+  if (!fe->timing) return;
+  while (fe->tev->size() < fe->tused + 2) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    fe->tev->push_back(e);
+  }
+  cudaEventRecord((*fe->tev)[fe->tused], fe->ctx->stream);
+  fe->tstage->push_back(stage);
+}
+static void fe_toc(sfe_frontend *fe) {
+  if (!fe->timing) return;
+  cudaEventRecord((*fe->tev)[fe->tused + 1], fe->ctx->stream);
+  fe->tused += 2;
+}
 
 extern "C" {
 
@@ -150,6 +174,8 @@ int sfe_frontend_create(sfe_ctx *ctx, const sfe_maps *maps, const sfe_frontend_p
   sfe_frontend *fe = new sfe_frontend();
   memset(fe, 0, sizeof(*fe));
   fe->ctx = ctx, fe->maps = maps, fe->p = *params, fe->max_frames = max_frames;
+  fe->tev = new std::vector<cudaEvent_t>();
+  fe->tstage = new std::vector<int>();
   const size_t F = max_frames, cap = params->cap_points, tcap = (size_t)params->window * cap;
   const size_t wpr = (params->B + 31) / 32;
   FE_ALLOC(fe->frames, F * params->R * params->B);
@@ -210,6 +236,11 @@ void sfe_frontend_destroy(sfe_frontend *fe) {
   for (auto &ev : fe->ev_copy)
     if (ev) cudaEventDestroy(ev);
   if (fe->ev_done) cudaEventDestroy(fe->ev_done);
+  if (fe->tev) {
+    for (auto e : *fe->tev) cudaEventDestroy(e);
+    delete fe->tev;
+  }
+  delete fe->tstage;
   delete fe;
 }
 
@@ -243,25 +274,33 @@ static int fe_features(sfe_frontend *fe, const uint8_t *frames_dev, int f0, int 
   const sfe_frontend_params &p = fe->p;
   const size_t cap = p.cap_points, wpr = (p.B + 31) / 32;
   uint32_t *bits = fe->bits + (size_t)f0 * p.R * wpr;
+  fe_tic(fe, SFE_FE_CFAR);
   int rc = cfar_run(ctx, frames_dev, SFE_U8, n, p.R, p.B, p.cfar_alg, p.train_hs, p.guard_hs, p.rank, p.tau,
                     p.gate_enable, p.gate_threshold, nullptr, nullptr, bits, 0);
+  fe_toc(fe);
   if (rc != SFE_OK) return rc;
+  fe_tic(fe, SFE_FE_CART);
   rc = cart_points_run(ctx, fe->maps, nullptr, bits, n, (int)cap, fe->ij + (size_t)f0 * cap * 2,
                        fe->xy_a + (size_t)f0 * cap * 2, fe->cnt_a + f0);
+  fe_toc(fe);
   if (rc != SFE_OK) return rc;
   // feature_extraction.py:241-249
   const float *cur = fe->xy_a;
   const int32_t *cur_cnt = fe->cnt_a;
   if (p.resolution > 0.f) {
+    fe_tic(fe, SFE_FE_DOWNSAMPLE);
     rc = downsample_run(ctx, cur, fe->off_pts + f0, cur_cnt + f0, n, 2, (int)cap, p.resolution, fe->xy_b, fe->idx,
                         fe->cnt_b + f0);
+    fe_toc(fe);
     if (rc != SFE_OK) return rc;
     cur = fe->xy_b, cur_cnt = fe->cnt_b;
   }
   if (p.outlier_min_points > 1) {
     float *dst = (cur == fe->xy_a) ? fe->xy_b : fe->xy_a;
+    fe_tic(fe, SFE_FE_OUTLIER);
     rc = remove_outlier_run(ctx, cur, fe->off_pts + f0, cur_cnt + f0, n, 2, (int)cap, p.outlier_radius,
                             p.outlier_min_points, dst, fe->idx, fe->cnt_c + f0);
+    fe_toc(fe);
     if (rc != SFE_OK) return rc;
   }
   return SFE_OK;
@@ -289,6 +328,7 @@ static int fe_match(sfe_frontend *fe, int n) {
   const int cap = p.cap_points, tcap = p.window * cap;
   const int32_t *cnt;
   const float *cloud = fe_cloud(fe, &cnt);
+  fe_tic(fe, SFE_FE_SUBMAP);
   assemble_targets_kernel<<<n, 256, 0, ctx->stream>>>(cloud, cnt, cap, fe->rel, n, p.window, fe->tgt_a, fe->tcnt_a,
                                                       tcap, fe->guess);
   SFE_CUDA(cudaGetLastError());
@@ -301,8 +341,41 @@ static int fe_match(sfe_frontend *fe, int n) {
     if (rc != SFE_OK) return rc;
     tgt = fe->tgt_b, tcnt = fe->tcnt_b;
   }
-  return icp_run(ctx, &p.icp, cloud, fe->off_pts, cnt, tgt, fe->off_tgt, tcnt, p.min_points, nullptr, nullptr, n,
-                 p.cap_source, p.cap_target, fe->guess, fe->T, fe->iters, fe->inliers, fe->status);
+  fe_toc(fe);
+  fe_tic(fe, SFE_FE_ICP);
+  int rc = icp_run(ctx, &p.icp, cloud, fe->off_pts, cnt, tgt, fe->off_tgt, tcnt, p.min_points, nullptr, nullptr, n,
+                   p.cap_source, p.cap_target, fe->guess, fe->T, fe->iters, fe->inliers, fe->status);
+  fe_toc(fe);
+  return rc;
+}
+
+int sfe_frontend_set_timing(sfe_frontend *fe, int enable) {
+  SFE_REQUIRE(fe != nullptr, "sfe_frontend_set_timing: null handle");
+  fe->timing = enable != 0;
+  fe->tused = 0;
+  fe->tstage->clear();
+  for (int i = 0; i < SFE_FE_STAGES; ++i) fe->stage_ms[i] = 0.0, fe->stage_launches[i] = 0;
+  return SFE_OK;
+}
+
+int sfe_frontend_get_timing(sfe_frontend *fe, double *stage_ms, int64_t *stage_calls) {
+  SFE_REQUIRE(fe && stage_ms, "sfe_frontend_get_timing: null argument");
+  SFE_CUDA(cudaSetDevice(fe->ctx->device));
+  SFE_CUDA(cudaStreamSynchronize(fe->ctx->stream));
+  for (size_t k = 0; k + 1 < fe->tused + 1 && 2 * k + 1 < fe->tused + 1 && k < fe->tstage->size(); ++k) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, (*fe->tev)[2 * k], (*fe->tev)[2 * k + 1]) == cudaSuccess) {
+      fe->stage_ms[(*fe->tstage)[k]] += ms;
+      fe->stage_launches[(*fe->tstage)[k]]++;
+    }
+  }
+  fe->tused = 0;
+  fe->tstage->clear();
+  for (int i = 0; i < SFE_FE_STAGES; ++i) {
+    stage_ms[i] = fe->stage_ms[i];
+    if (stage_calls) stage_calls[i] = fe->stage_launches[i];
+  }
+  return SFE_OK;
 }
 
 int sfe_frontend_run_dev(sfe_frontend *fe, const uint8_t *frames_dev, const double *poses_host, int n_frames) {

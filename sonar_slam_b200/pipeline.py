@@ -67,6 +67,18 @@ class FrontEnd:
         d["cloud_stride"] = stride.value
         return d
 
+    STAGES = ("cfar", "cart_points", "downsample", "remove_outlier", "submap", "icp")
+
+    def set_timing(self, enable=True):
+        _lib.check(self.lib.sfe_frontend_set_timing(self.handle, 1 if enable else 0), "sfe_frontend_set_timing")
+
+    def get_timing(self):
+        """dict stage -> (total ms, number of timed intervals) since set_timing(True)."""
+        ms = np.zeros(len(self.STAGES), np.float64)
+        calls = np.zeros(len(self.STAGES), np.int64)
+        _lib.check(self.lib.sfe_frontend_get_timing(self.handle, _lib.ptr(ms), _lib.ptr(calls)), "sfe_frontend_get_timing")
+        return {k: (float(ms[i]), int(calls[i])) for i, k in enumerate(self.STAGES)}
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.sfe_frontend_destroy(self.handle)
