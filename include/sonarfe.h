@@ -224,7 +224,8 @@ typedef struct {
   float submap_resolution;  /* slam.yaml point_resolution (0.5; <= 0: no down-sampling of the target) */
   int min_points;           /* slam.yaml ssm/min_points (50) */
   sfe_icp_params icp;
-  int cap_points;           /* capacity (rows) reserved per frame for its Cartesian cloud */
+  int cap_points;           /* capacity (rows) reserved per frame for its Cartesian cloud; a frame with more
+                               detections is truncated and reported as SFE_ICP_TOO_LARGE */
   int cap_source, cap_target; /* largest source / target cloud the scan matcher accepts */
 } sfe_frontend_params;
 SFE_API void sfe_frontend_params_default(sfe_frontend_params *p);

@@ -59,6 +59,8 @@ struct sfe_maps {  // per-geometry polar->Cartesian sampling table (featx.cu)
   int R, B;        // polar image
   double width, height;
   void *table;     // device MapEntry[rows*cols]
+  int32_t *inv_off;  // device [R*B + 1]: for every polar cell, the Cartesian pixels it can light ...
+  int32_t *inv_idx;  // ... as a CSR list of pixel indices
   int device;
 };
 

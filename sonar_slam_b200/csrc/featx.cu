@@ -25,6 +25,34 @@
 
 namespace sfe {
 
+__device__ __forceinline__ int block_exclusive_scan_fx(int v, int *warp_sums /* [33] */, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < nwarps ? warp_sums[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
+    }
+    warp_sums[lane] = wi - w;
+    if (lane == 31) warp_sums[32] = wi;
+  }
+  __syncthreads();
+  const int excl = warp_sums[warp] + incl - v;
+  total = warp_sums[32];
+  __syncthreads();
+  return excl;
+}
+
 struct __align__(8) MapEntry {
   int16_t ix, iy;   // top-left tap (saturated like cv::saturate_cast<short>)
   uint8_t fx, fy;   // 1/32-pixel fractions
@@ -33,6 +61,118 @@ struct __align__(8) MapEntry {
 };
 
 constexpr int FX_THREADS = 1024;
+constexpr int FXS_THREADS = 512;  // detection-driven variant
+
+// cv2.remap's fixed-point bilinear rule for one Cartesian pixel against a 0/1 polar bit plane
+__device__ __forceinline__ bool cart_pixel_fires(const MapEntry e, const uint32_t *__restrict__ sb, int R, int B, int wpr) {
+  const int ix = e.ix, iy = e.iy, fx = e.fx, fy = e.fy;
+  const bool x0 = (unsigned)ix < (unsigned)B, x1 = (unsigned)(ix + 1) < (unsigned)B;
+  const bool y0 = (unsigned)iy < (unsigned)R, y1 = (unsigned)(iy + 1) < (unsigned)R;
+  const int w00 = (x0 && y0) ? (32 - fx) * (32 - fy) : 0, w01 = (x1 && y0) ? fx * (32 - fy) : 0;
+  const int w10 = (x0 && y1) ? (32 - fx) * fy : 0, w11 = (x1 && y1) ? fx * fy : 0;
+  const int cx0 = x0 ? ix : 0, cx1 = x1 ? ix + 1 : 0, cy0 = y0 ? iy : 0, cy1 = y1 ? iy + 1 : 0;
+  const int sum = w00 * (int)((sb[cy0 * wpr + (cx0 >> 5)] >> (cx0 & 31)) & 1u) +
+                  w01 * (int)((sb[cy0 * wpr + (cx1 >> 5)] >> (cx1 & 31)) & 1u) +
+                  w10 * (int)((sb[cy1 * wpr + (cx0 >> 5)] >> (cx0 & 31)) & 1u) +
+                  w11 * (int)((sb[cy1 * wpr + (cx1 >> 5)] >> (cx1 & 31)) & 1u);
+  return sum >= 512;
+}
+
+__device__ __forceinline__ void cart_emit(int pix, int cols, int rows, double width, double height, int32_t *ij,
+                                          float *xy, size_t o) {
+  const int row = pix / cols, col = pix - row * cols;
+  ij[o] = row;
+  ij[o + 1] = col;
+  // feature_extraction.py:235-237, float64, operation by operation (no contraction)
+  double x = __dsub_rn((double)col, __ddiv_rn((double)cols, 2.0));
+  x = __dmul_rn(__ddiv_rn(x, __ddiv_rn((double)cols, 2.0)), __ddiv_rn(width, 2.0));
+  x = __dmul_rn(-1.0, x);
+  double y = __dmul_rn(-1.0, __ddiv_rn((double)row, (double)rows));
+  y = __dadd_rn(__dmul_rn(y, height), height);
+  xy[o] = (float)y;
+  xy[o + 1] = (float)x;
+}
+
+// Detection-driven variant.  A Cartesian pixel can only be non-zero if one of its four taps is a
+// detection, and detections are sparse (~0.5 % of the polar image), so instead of testing all rows*cols
+// pixels the CTA walks the set bits of the polar plane and, for each, the precomputed list of Cartesian
+// pixels that sample it; firing pixels are marked in a Cartesian bit plane in shared memory, which is then
+// scanned once, in order, to emit the points (np.nonzero order).  One CTA per frame.
+__global__ void __launch_bounds__(FXS_THREADS)
+    cart_scatter_kernel(const MapEntry *__restrict__ tab, const int32_t *__restrict__ inv_off,
+                        const int32_t *__restrict__ inv_idx, int npix, int cols, int rows, int R, int B, int wpr,
+                        const uint8_t *__restrict__ mask, const uint32_t *__restrict__ bits, int F, int cap,
+                        double width, double height, int32_t *__restrict__ ij, float *__restrict__ xy,
+                        int32_t *__restrict__ count) {
+  extern __shared__ uint32_t fxs_smem[];
+  __shared__ int scan_s[36];
+  const int words = R * wpr, cwords = (npix + 31) / 32;
+  uint32_t *sb = fxs_smem;           // polar bit plane
+  uint32_t *cm = fxs_smem + words;   // Cartesian bit plane
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = FXS_THREADS / 32;
+
+  for (int f = blockIdx.x; f < F; f += gridDim.x) {
+    __syncthreads();
+    if (bits != nullptr) {
+      const uint32_t *src = bits + (size_t)f * words;
+      for (int w = tid; w < words; w += FXS_THREADS) sb[w] = src[w];
+    } else {
+      const uint8_t *src = mask + (size_t)f * R * B;
+      for (int w = tid; w < words; w += FXS_THREADS) {
+        const int r = w / wpr, q = w - r * wpr;
+        const uint8_t *row = src + (size_t)r * B + q * 32;
+        const int nb = min(32, B - q * 32);
+        uint32_t word = 0;
+        for (int t = 0; t < nb; ++t) word |= (row[t] ? 1u : 0u) << t;
+        sb[w] = word;
+      }
+    }
+    for (int w = tid; w < cwords; w += FXS_THREADS) cm[w] = 0;
+    __syncthreads();
+    // ---- walk the detections: a warp takes 32 polar words at a time, then one detection at a time
+    for (int base = warp * 32; base < words; base += nwarps * 32) {
+      const int wi_mine = base + lane;
+      const uint32_t mine = wi_mine < words ? sb[wi_mine] : 0u;
+      unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
+      while (nz) {
+        const int l = __ffs(nz) - 1;
+        nz &= nz - 1;
+        uint32_t wbits = __shfl_sync(0xffffffffu, mine, l);
+        const int wi = base + l, y = wi / wpr, xq = (wi - y * wpr) * 32;
+        while (wbits) {
+          const int bit = __ffs(wbits) - 1;
+          wbits &= wbits - 1;
+          const int x = xq + bit;
+          if (x >= B) break;
+          const int q = y * B + x;
+          const int s = inv_off[q], e = inv_off[q + 1];
+          for (int t = s + lane; t < e; t += 32) {
+            const int pix = inv_idx[t];
+            if (cart_pixel_fires(tab[pix], sb, R, B, wpr)) atomicOr(&cm[pix >> 5], 1u << (pix & 31));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- ordered emission: every thread owns a contiguous run of Cartesian words
+    const int per = (cwords + FXS_THREADS - 1) / FXS_THREADS;
+    const int w0 = min(tid * per, cwords), w1 = min(w0 + per, cwords);
+    int mine_cnt = 0;
+    for (int w = w0; w < w1; ++w) mine_cnt += __popc(cm[w]);
+    int total;
+    int idx = block_exclusive_scan_fx(mine_cnt, scan_s, total);
+    for (int w = w0; w < w1; ++w) {
+      uint32_t v = cm[w];
+      while (v) {
+        const int bit = __ffs(v) - 1;
+        v &= v - 1;
+        if (idx < cap) cart_emit(w * 32 + bit, cols, rows, width, height, ij, xy, ((size_t)f * cap + idx) * 2);
+        ++idx;
+      }
+    }
+    if (tid == 0) count[f] = total;
+  }
+}
 
 template <int FPB>
 __global__ void __launch_bounds__(FX_THREADS)
@@ -169,6 +309,11 @@ __global__ void __launch_bounds__(FX_THREADS)
   }
 }
 
+static bool ctx_force_gather(const sfe_ctx *) {
+  const char *e = getenv("SFE_CART_DENSE");  // development switch: force the dense kernel
+  return e && e[0] == '1';
+}
+
 template <int FPB>
 static int launch_cart(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const uint32_t *bits, int F, int cap,
                        int32_t *ij, float *xy, int32_t *count) {
@@ -195,7 +340,25 @@ int cart_points_run(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const 
   SFE_REQUIRE(F >= 0 && cap >= 0, "cart_points: negative frame count or capacity");
   SFE_REQUIRE(F == 0 || (ij && xy && count), "cart_points: null output pointer");
   if (F == 0) return SFE_OK;
-  // several frames per CTA amortise the table read once there are enough frames to fill the GPU
+  // detection-driven kernel whenever both bit planes fit in shared memory
+  {
+    const int wpr = (m->B + 31) / 32, npix = m->rows * m->cols;
+    const size_t smem = sizeof(uint32_t) * ((size_t)m->R * wpr + (size_t)(npix + 31) / 32);
+    if (m->inv_off != nullptr && smem <= (size_t)ctx->max_smem_optin - 2048 && !ctx_force_gather(ctx)) {
+      SFE_CUDA(cudaFuncSetAttribute(cart_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1;
+      SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cart_scatter_kernel, FXS_THREADS, smem));
+      int grid = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+      if (grid > F) grid = F;
+      cart_scatter_kernel<<<grid, FXS_THREADS, smem, ctx->stream>>>(
+          (const MapEntry *)m->table, m->inv_off, m->inv_idx, npix, m->cols, m->rows, m->R, m->B, wpr, mask, bits, F,
+          cap, m->width, m->height, ij, xy, count);
+      SFE_CUDA(cudaGetLastError());
+      ctx->launches++;
+      return SFE_OK;
+    }
+  }
+  // dense variant: several frames per CTA amortise the table read once there are enough frames
   int rc = SFE_ERR_UNSUPPORTED;
   if (F >= 4 * ctx->sm_count) rc = launch_cart<4>(ctx, m, mask, bits, F, cap, ij, xy, count);
   if (rc == SFE_ERR_UNSUPPORTED && F >= 2 * ctx->sm_count) rc = launch_cart<2>(ctx, m, mask, bits, F, cap, ij, xy, count);
@@ -239,13 +402,40 @@ int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_ho
     }
     tab[p] = e;
   }
+  // inverse lists: polar cell -> Cartesian pixels that sample it with non-zero weight
+  std::vector<int32_t> inv_off((size_t)R * B + 1, 0);
+  auto each_tap = [&](size_t p, auto &&fn) {
+    const MapEntry &e = tab[p];
+    if (!(e.flags & 1)) return;
+    const int wts[4] = {(32 - e.fx) * (32 - e.fy), e.fx * (32 - e.fy), (32 - e.fx) * e.fy, e.fx * e.fy};
+    for (int t = 0; t < 4; ++t) {
+      const int x = e.ix + (t & 1), y = e.iy + (t >> 1);
+      if (wts[t] > 0 && x >= 0 && x < B && y >= 0 && y < R) fn((size_t)y * B + x);
+    }
+  };
+  for (size_t p = 0; p < n; ++p) each_tap(p, [&](size_t q) { inv_off[q + 1]++; });
+  for (size_t q = 0; q < (size_t)R * B; ++q) inv_off[q + 1] += inv_off[q];
+  std::vector<int32_t> inv_idx((size_t)inv_off.back() + 1);
+  {
+    std::vector<int32_t> cur(inv_off.begin(), inv_off.end() - 1);
+    for (size_t p = 0; p < n; ++p) each_tap(p, [&](size_t q) { inv_idx[cur[q]++] = (int32_t)p; });
+  }
   sfe_maps *m = new sfe_maps();
   m->rows = rows, m->cols = cols, m->R = R, m->B = B, m->width = width, m->height = height, m->device = ctx->device;
+  m->table = nullptr, m->inv_off = nullptr, m->inv_idx = nullptr;
   cudaError_t e = cudaMalloc(&m->table, n * sizeof(MapEntry));
   if (e == cudaSuccess) e = cudaMemcpy(m->table, tab.data(), n * sizeof(MapEntry), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&m->inv_off, inv_off.size() * sizeof(int32_t));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->inv_off, inv_off.data(), inv_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&m->inv_idx, inv_idx.size() * sizeof(int32_t));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->inv_idx, inv_idx.data(), inv_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     set_error("sfe_maps_create: %s", cudaGetErrorString(e));
     if (m->table) cudaFree(m->table);
+    if (m->inv_off) cudaFree(m->inv_off);
+    if (m->inv_idx) cudaFree(m->inv_idx);
     delete m;
     return SFE_ERR_CUDA;
   }
@@ -257,6 +447,8 @@ void sfe_maps_destroy(sfe_maps *m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->table) cudaFree(m->table);
+  if (m->inv_off) cudaFree(m->inv_off);
+  if (m->inv_idx) cudaFree(m->inv_idx);
   delete m;
 }
 

@@ -34,6 +34,8 @@ struct IcpBatch {
   const int *src_cnt;  // optional counts (else off[c+1]-off[c])
   const int *tgt_cnt;
   int min_points;      // problems whose source or target has fewer points are skipped (ICP_SKIPPED)
+  const int *raw_cnt;  // optional: un-clamped size of the source's raw cloud; > raw_cap -> ICP_TOO_LARGE
+  int raw_cap;
   const int *src_id;  // may be null (problem p uses source p)
   const int *tgt_id;  // may be null
   const float *guess; // [P][9] row-major 3x3
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
     // ---- admission checks (thread 0), failure leaves T = guess
     if (tid == 0) {
       int st = ICP_OK;
-      if (ns > b.ns_max || nt > b.nt_max) st = ICP_TOO_LARGE;
+      if (ns > b.ns_max || nt > b.nt_max || (b.raw_cnt && b.raw_cnt[si] > b.raw_cap)) st = ICP_TOO_LARGE;
       else if (ns < b.min_points || nt < b.min_points) st = ICP_SKIPPED;
       else if (nt <= 0) st = ICP_EMPTY_REF;
       const float det = __fsub_rn(__fmul_rn(guess[0], guess[4]), __fmul_rn(guess[1], guess[3]));
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
           if (kk >= total_fin) kk = total_fin - 1;
           uint32_t prefix = 0, mask = 0;
           for (int shift = 24; shift >= 0; shift -= 8) {
-            if (tid < 256) sh.hist[tid] = 0;
+            for (int h = tid; h < 256; h += nthr) sh.hist[h] = 0;
             __syncthreads();
             for (int i = tid; i < ns; i += nthr) {
               if (match[i] == 0xffff) continue;
@@ -506,7 +508,7 @@ static int pick_max_cells(int nt_max) {
 int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
             const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
             const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,
-            int *inliers, int *status) {
+            int *inliers, int *status, const int *raw_cnt, int raw_cap) {
   SFE_REQUIRE(ctx && prm, "icp: null context or parameters");
   SFE_REQUIRE(P >= 0 && ns_max >= 0 && nt_max >= 0, "icp: negative sizes");
   if (P == 0) return SFE_OK;
@@ -518,6 +520,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   IcpBatch b{};
   b.src_pts = src_pts, b.src_off = src_off, b.tgt_pts = tgt_pts, b.tgt_off = tgt_off;
   b.src_cnt = src_cnt, b.tgt_cnt = tgt_cnt, b.min_points = min_points;
+  b.raw_cnt = raw_cnt, b.raw_cap = raw_cap;
   b.src_id = src_id, b.tgt_id = tgt_id, b.guess = guess;
   b.T_out = T_out, b.iters = iters, b.inliers = inliers, b.status = status;
   b.P = P, b.ns_max = ns_max > 0 ? ns_max : 1, b.nt_max = nt_max > 0 ? nt_max : 1;
@@ -532,15 +535,17 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
     return SFE_ERR_UNSUPPORTED;
   }
   SFE_CUDA(cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // CTA size follows the source size (one NN query per thread and iteration is the sweet spot)
+  const int threads = b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS);
   int per_sm = 1;
-  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, ICP_THREADS, smem));
+  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, threads, smem));
   if (per_sm < 1) per_sm = 1;
   int grid = ctx->sm_count * per_sm;
   if (grid > P) grid = P;
   int rc = ensure(ctx, ctx->scratch[SCR_ICP], (size_t)grid * b.nt_max * sizeof(uint16_t));
   if (rc != SFE_OK) return rc;
   b.orig_ws = (uint16_t *)ctx->scratch[SCR_ICP].ptr;
-  icp_kernel<<<grid, ICP_THREADS, smem, ctx->stream>>>(b);
+  icp_kernel<<<grid, threads, smem, ctx->stream>>>(b);
   SFE_CUDA(cudaGetLastError());
   ctx->launches++;
   return SFE_OK;

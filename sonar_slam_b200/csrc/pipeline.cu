@@ -29,7 +29,7 @@ int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int
 int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
             const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
             const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,
-            int *inliers, int *status);
+            int *inliers, int *status, const int *raw_cnt = nullptr, int raw_cap = 0);
 
 // T_ab = pose_a^-1 * pose_b as float32 3x3 (gtsam Pose2::between, then matrix().astype(float32)).
 // Evaluated on the host in double (libm), so the float32 matrices the kernels see are the ones a
@@ -146,8 +146,8 @@ void sfe_frontend_params_default(sfe_frontend_params *p) {
   p->submap_resolution = 0.5f;
   p->min_points = 50;
   sfe_icp_params_default(&p->icp);
-  p->cap_points = 4096;
-  p->cap_source = 2048, p->cap_target = 6144;
+  p->cap_points = 8192;
+  p->cap_source = 1024, p->cap_target = 3072;
 }
 
 #define FE_ALLOC(ptr, bytes)                                                        \
@@ -344,7 +344,7 @@ static int fe_match(sfe_frontend *fe, int n) {
   fe_toc(fe);
   fe_tic(fe, SFE_FE_ICP);
   int rc = icp_run(ctx, &p.icp, cloud, fe->off_pts, cnt, tgt, fe->off_tgt, tcnt, p.min_points, nullptr, nullptr, n,
-                   p.cap_source, p.cap_target, fe->guess, fe->T, fe->iters, fe->inliers, fe->status);
+                   p.cap_source, p.cap_target, fe->guess, fe->T, fe->iters, fe->inliers, fe->status, fe->cnt_a, cap);
   fe_toc(fe);
   return rc;
 }

@@ -147,7 +147,7 @@ def make_trajectory_frames(n_frames, seed=0, num_ranges=512, num_beams=512, max_
     if bearings is None:
         bearings = bearings_oculus(num_beams)
     b_rad = np.deg2rad(bearings.astype(np.float64) / 100.0)
-    walls = make_walls(rng, n_segments=30, extent=90.0, min_len=15.0, max_len=45.0)
+    walls = make_walls(rng, n_segments=24, extent=90.0, min_len=15.0, max_len=45.0)
     seg_len = np.hypot(walls[:, 2] - walls[:, 0], walls[:, 3] - walls[:, 1])
     pts, amp = [], []
     for w, L in zip(walls, seg_len):

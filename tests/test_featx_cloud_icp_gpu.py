@@ -56,6 +56,21 @@ def test_cart_points_batches_random_masks_vs_cv2(gpu_ctx):
     assert np.array_equal(small["ij"][1].cpu().numpy(), out["ij"][1, :10].cpu().numpy())
 
 
+def test_cart_points_dense_and_detection_driven_kernels_agree(gpu_ctx, monkeypatch):
+    geo = _geo("uniform")
+    maps = _maps(gpu_ctx, geo, 512, 512)
+    imgs = torch.from_numpy(synth.make_frames(range(40, 46))).cuda()
+    det = ops.cfar(imgs, "SOCA", 20, 5, TAU_SOCA, gate=65, want_bits=True)
+    a = ops.cart_points(maps, bits=det["bits"], capacity=6000)
+    monkeypatch.setenv("SFE_CART_DENSE", "1")
+    b = ops.cart_points(maps, mask=det["mask"], capacity=6000)
+    monkeypatch.delenv("SFE_CART_DENSE")
+    assert torch.equal(a["count"], b["count"]) and int(a["count"].min()) > 100
+    for f in range(6):
+        k = int(a["count"][f])
+        assert torch.equal(a["ij"][f, :k], b["ij"][f, :k]) and torch.equal(a["xy"][f, :k], b["xy"][f, :k])
+
+
 def test_cart_points_odd_geometry(gpu_ctx):
     geo = featx_ref.Geometry(0.1, 200, np.round(np.linspace(-3000, 3500, 96)).astype(np.int16))
     maps = _maps(gpu_ctx, geo, 200, 96)
