@@ -62,6 +62,8 @@ struct __align__(8) MapEntry {
 
 constexpr int FX_THREADS = 1024;
 constexpr int FXS_THREADS = 512;  // detection-driven variant
+constexpr int FXS_PER_THREAD = 8;                        // detections a thread lists per round
+constexpr int FXS_DET_SLOTS = FXS_PER_THREAD * FXS_THREADS;
 
 // cv2.remap's fixed-point bilinear rule for one Cartesian pixel against a 0/1 polar bit plane
 __device__ __forceinline__ bool cart_pixel_fires(const MapEntry e, const uint32_t *__restrict__ sb, int R, int B, int wpr) {
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(FXS_THREADS)
   const int words = R * wpr, cwords = (npix + 31) / 32;
   uint32_t *sb = fxs_smem;           // polar bit plane
   uint32_t *cm = fxs_smem + words;   // Cartesian bit plane
+  int32_t *det = reinterpret_cast<int32_t *>(fxs_smem + words + cwords);  // [FXS_DET_SLOTS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = FXS_THREADS / 32;
 
   for (int f = blockIdx.x; f < F; f += gridDim.x) {
@@ -129,28 +132,52 @@ __global__ void __launch_bounds__(FXS_THREADS)
     }
     for (int w = tid; w < cwords; w += FXS_THREADS) cm[w] = 0;
     __syncthreads();
-    // ---- walk the detections: a warp takes 32 polar words at a time, then one detection at a time
-    for (int base = warp * 32; base < words; base += nwarps * 32) {
-      const int wi_mine = base + lane;
-      const uint32_t mine = wi_mine < words ? sb[wi_mine] : 0u;
-      unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
-      while (nz) {
-        const int l = __ffs(nz) - 1;
-        nz &= nz - 1;
-        uint32_t wbits = __shfl_sync(0xffffffffu, mine, l);
-        const int wi = base + l, y = wi / wpr, xq = (wi - y * wpr) * 32;
-        while (wbits) {
-          const int bit = __ffs(wbits) - 1;
-          wbits &= wbits - 1;
-          const int x = xq + bit;
-          if (x >= B) break;
-          const int q = y * B + x;
-          const int s = inv_off[q], e = inv_off[q + 1];
-          for (int t = s + lane; t < e; t += 32) {
+    // ---- list the detections (polar cell indices) in shared memory, FXS_DETCAP per round (8 per thread),
+    //      then spread (detection -> candidate pixels) work evenly over the CTA: every lane has its own
+    //      chain of loads in flight instead of a warp serialising on one detection.
+    {
+      // a thread owns words tid, tid + T, tid + 2T, ...: neighbouring words (an arc of detections spans a
+      // few of them in a few rows) land on different threads
+      int w = tid;
+      uint32_t v = w < words ? sb[w] : 0u;
+      while (true) {
+        // count up to FXS_PER_THREAD of my remaining detections
+        int take = 0;
+        {
+          int wc = w;
+          uint32_t vc = v;
+          while (take < FXS_PER_THREAD) {
+            if (vc == 0u) {
+              wc += FXS_THREADS;
+              if (wc >= words) break;
+              vc = sb[wc];
+              continue;
+            }
+            vc &= vc - 1;
+            ++take;
+          }
+        }
+        int total;
+        int pos = block_exclusive_scan_fx(take, scan_s, total);
+        if (total == 0) break;
+        for (int i = 0; i < take; ++i) {
+          while (v == 0u) v = sb[w += FXS_THREADS];
+          const int bit = __ffs(v) - 1;
+          v &= v - 1;
+          const int y = w / wpr, x = (w - y * wpr) * 32 + bit;
+          det[pos++] = x < B ? y * B + x : -1;
+        }
+        __syncthreads();
+        for (int d = tid; d < total; d += FXS_THREADS) {
+          const int q = det[d];
+          if (q < 0) continue;
+          const int s0 = inv_off[q], e0 = inv_off[q + 1];
+          for (int t = s0; t < e0; ++t) {
             const int pix = inv_idx[t];
             if (cart_pixel_fires(tab[pix], sb, R, B, wpr)) atomicOr(&cm[pix >> 5], 1u << (pix & 31));
           }
         }
+        __syncthreads();
       }
     }
     __syncthreads();
@@ -161,15 +188,22 @@ __global__ void __launch_bounds__(FXS_THREADS)
     for (int w = w0; w < w1; ++w) mine_cnt += __popc(cm[w]);
     int total;
     int idx = block_exclusive_scan_fx(mine_cnt, scan_s, total);
+    // pass 1: pixel indices in order (cheap, but unevenly spread over threads) ...
+    int32_t *ij_f = ij + (size_t)f * cap * 2;
     for (int w = w0; w < w1; ++w) {
       uint32_t v = cm[w];
       while (v) {
         const int bit = __ffs(v) - 1;
         v &= v - 1;
-        if (idx < cap) cart_emit(w * 32 + bit, cols, rows, width, height, ij, xy, ((size_t)f * cap + idx) * 2);
+        if (idx < cap) ij_f[2 * (size_t)idx] = w * 32 + bit;
         ++idx;
       }
     }
+    __syncthreads();
+    // ... pass 2: (row, col) and metres, evenly spread
+    const int n_out = min(total, cap);
+    for (int i = tid; i < n_out; i += FXS_THREADS)
+      cart_emit(ij_f[2 * (size_t)i], cols, rows, width, height, ij, xy, ((size_t)f * cap + i) * 2);
     if (tid == 0) count[f] = total;
   }
 }
@@ -343,7 +377,7 @@ int cart_points_run(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const 
   // detection-driven kernel whenever both bit planes fit in shared memory
   {
     const int wpr = (m->B + 31) / 32, npix = m->rows * m->cols;
-    const size_t smem = sizeof(uint32_t) * ((size_t)m->R * wpr + (size_t)(npix + 31) / 32);
+    const size_t smem = sizeof(uint32_t) * ((size_t)m->R * wpr + (size_t)(npix + 31) / 32 + FXS_DET_SLOTS);
     if (m->inv_off != nullptr && smem <= (size_t)ctx->max_smem_optin - 2048 && !ctx_force_gather(ctx)) {
       SFE_CUDA(cudaFuncSetAttribute(cart_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 1;
