@@ -34,6 +34,8 @@
 //      (ascending range, one float32 accumulator per sum) and evaluates the
 //      threshold in double exactly as written in cfar.cpp, so it is bit-exact for
 //      arbitrary float32 images.  It is a device path, not a CPU fallback.
+#include <vector>
+
 #include "common.cuh"
 
 namespace sfe {
@@ -335,6 +337,159 @@ __global__ void __launch_bounds__(CF_W + 32, 3)
   if (MASK && tid == 0) tma_wait_all<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// uint8 streaming kernel: the node's native image type (feature_extraction.py:217).  Same TMA ring and
+// per-beam register rings as above, but everything is integer: window sums are exact int32, and the
+// reference's double-precision compare `(double)x > tau * S / div` (and the amplitude gate) is folded
+// into a table M[S] = smallest cell value that passes for window statistic S, built on the host with
+// the reference's own double expression for every possible S (S <= 2*T*255).  Per cell: one add/sub,
+// one min/max, one table look-up in shared memory, one compare -- no floating point, no ambiguity path.
+constexpr int CF_LUT_MAX = 2 * CF_T * 255 + 1;  // CA: sum of 40 uint8 cells
+
+struct CfarStepI {
+  int xr[CF_RING];
+  int wr[CF_RING];
+  int w;
+};
+
+template <int ALG, bool MASK, bool BITS, bool EDGE, int J>
+__device__ __forceinline__ void cfar_step_u8(CfarStepI &s, const int xn, uint8_t (*obuf_ob)[CF_W],
+                                             const uint16_t *__restrict__ lut, const int R, const int r,
+                                             const int tid, const bool col_ok, unsigned &keep_bits) {
+  constexpr int I = J % CF_CH;
+  const int x20 = s.xr[(J + CF_RING - CF_T) % CF_RING];
+  const int xc = s.xr[(J + CF_RING - CF_HALF) % CF_RING];
+  const int lead = s.wr[(J + CF_RING - (CF_HALF + CF_G + 1)) % CF_RING];
+  const int lag = s.w + xn - x20;
+  s.w = lag;
+  s.wr[J % CF_RING] = lag;
+  s.xr[J % CF_RING] = xn;
+  bool pass = false;
+  if (!EDGE || (r >= CF_HALF && r < R - CF_HALF)) {
+    const int S = ALG == SFE_CFAR_CA ? lead + lag : (ALG == SFE_CFAR_SOCA ? min(lead, lag) : max(lead, lag));
+    pass = xc >= (int)lut[S];
+  }
+  if (MASK) obuf_ob[I][tid] = pass ? 1 : 0;
+  if (BITS) {
+    const unsigned b = __ballot_sync(0xffffffffu, pass && col_ok);
+    if ((tid & 31) == I) keep_bits = b;  // lane i keeps the ballot of output row i
+  }
+}
+
+template <int ALG, bool MASK, bool BITS, bool EDGE, int Q>
+__device__ __forceinline__ void cfar_block16_u8(CfarStepI &s, uint8_t (*tile)[CF_CH][CF_W],
+                                                uint8_t (*obuf)[CF_CH][CF_W], uint32_t (*obits)[CF_CH][CF_W / 32],
+                                                uint64_t *full_bar, uint64_t *empty_bar, const uint16_t *lut,
+                                                const CfarParams &p, const int blk, const int nchunks,
+                                                const int tid, const int f, const int col0) {
+  const int r0 = (blk - 2) * CF_CH;
+  const int cA = blk - 1, cB = blk;
+  const bool hasA = EDGE ? (cA >= 0 && cA < nchunks) : true;
+  const bool hasB = EDGE ? (cB < nchunks) : true;
+  const uint8_t(*tileA)[CF_W] = tile[cA & (CF_NSTAGE - 1)];
+  const uint8_t(*tileB)[CF_W] = tile[cB & (CF_NSTAGE - 1)];
+  constexpr int ob = Q & 1;
+  const bool col_ok = col0 + tid < p.B;
+  unsigned keep_bits = 0;
+  int xin[CF_CH];
+#pragma unroll
+  for (int i = 0; i < CF_SPLIT; ++i) xin[i] = (!EDGE || hasA) ? (int)tileA[i + CF_CH - CF_SPLIT][tid] : 0;
+  if (hasB) mbar_wait(&full_bar[cB & (CF_NSTAGE - 1)], (cB / CF_NSTAGE) & 1);
+#pragma unroll
+  for (int i = CF_SPLIT; i < CF_CH; ++i) xin[i] = (!EDGE || hasB) ? (int)tileB[i - CF_SPLIT][tid] : 0;
+  if (hasA) {
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty_bar[cA & (CF_NSTAGE - 1)]);
+  }
+#define SFE_STEP(I) \
+  cfar_step_u8<ALG, MASK, BITS, EDGE, Q * CF_CH + I>(s, xin[I], obuf[ob], lut, p.R, r0 + I, tid, col_ok, keep_bits);
+  SFE_STEP(0) SFE_STEP(1) SFE_STEP(2) SFE_STEP(3) SFE_STEP(4) SFE_STEP(5) SFE_STEP(6) SFE_STEP(7)
+  SFE_STEP(8) SFE_STEP(9) SFE_STEP(10) SFE_STEP(11) SFE_STEP(12) SFE_STEP(13) SFE_STEP(14) SFE_STEP(15)
+#undef SFE_STEP
+  if (EDGE && r0 < 0) return;
+  if (BITS && (tid & 31) < CF_CH) obits[ob][tid & 31][tid >> 5] = keep_bits;
+  if (MASK) fence_proxy_async_smem();
+  if (MASK && tid == 0) tma_wait_read<0>();
+  named_bar_sync(1, CF_W);
+  if (MASK && tid == 0) {
+    tma_store_3d(p.out_map, &obuf[ob][0][0], col0, r0, f);
+    tma_commit();
+  }
+  if (BITS && tid < CF_CH * (CF_W / 32)) {
+    const int i = tid / (CF_W / 32), wq = tid % (CF_W / 32);
+    const int w = (col0 >> 5) + wq;
+    if (r0 + i < p.R && w < p.words_per_row)
+      p.bits[((size_t)f * p.R + r0 + i) * p.words_per_row + w] = obits[ob][i][wq];
+  }
+}
+
+template <int ALG, bool MASK, bool BITS>
+__global__ void __launch_bounds__(CF_W + 32, 4)
+    cfar_u8_lut_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                       CfarParams p, const uint16_t *__restrict__ lut_g, const int lut_n) {
+  __shared__ __align__(128) uint8_t tile[CF_NSTAGE][CF_CH][CF_W];
+  __shared__ __align__(128) uint8_t obuf[2][CF_CH][CF_W];
+  __shared__ uint32_t obits[2][CF_CH][CF_W / 32];
+  __shared__ __align__(8) uint64_t full_bar[CF_NSTAGE];
+  __shared__ __align__(8) uint64_t empty_bar[CF_NSTAGE];
+  __shared__ __align__(16) uint16_t lut[(ALG == SFE_CFAR_CA ? CF_LUT_MAX : CF_T * 255 + 1) + 7];
+
+  const int tid = threadIdx.x;
+  const int f = blockIdx.x / p.strips;
+  const int col0 = (blockIdx.x % p.strips) * CF_W;
+  const int R = p.R;
+  p.out_map = &out_map;
+  const int nchunks = (R + CF_CH - 1) / CF_CH;
+
+  if (tid == 0) {
+    for (int st = 0; st < CF_NSTAGE; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], CF_W / 32);
+    }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < lut_n; i += CF_W + 32) lut[i] = lut_g[i];
+  __syncthreads();
+
+  if (tid >= CF_W) {
+    if (tid == CF_W) {
+      prefetch_tmap(&in_map);
+      for (int c = 0; c < nchunks; ++c) {
+        const int st = c % CF_NSTAGE, it = c / CF_NSTAGE;
+        if (it > 0) mbar_wait(&empty_bar[st], (it - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[st], CF_CH * CF_W);
+        tma_load_3d(&tile[st][0][0], &in_map, &full_bar[st], col0, c * CF_CH, f);
+      }
+    }
+    return;
+  }
+
+  CfarStepI s;
+#pragma unroll
+  for (int i = 0; i < CF_RING; ++i) s.xr[i] = 0, s.wr[i] = 0;
+  s.w = 0;
+  const int nblk = nchunks + 2;
+  for (int b2 = 0; b2 * 2 < nblk; ++b2) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int blk = b2 * 2 + q;
+      if (blk < nblk) {
+        const int r0 = (blk - 2) * CF_CH;
+        const bool interior = (r0 >= CF_HALF) && (r0 + CF_CH - 1 < R - CF_HALF);
+#define SFE_BLOCK(EDGE_, Q_) \
+  cfar_block16_u8<ALG, MASK, BITS, EDGE_, Q_>(s, tile, obuf, obits, full_bar, empty_bar, lut, p, blk, nchunks, tid, f, col0)
+        if (interior) {
+          if (q == 0) SFE_BLOCK(false, 0); else SFE_BLOCK(false, 1);
+        } else {
+          if (q == 0) SFE_BLOCK(true, 0); else SFE_BLOCK(true, 1);
+        }
+#undef SFE_BLOCK
+      }
+    }
+  }
+  if (MASK && tid == 0) tma_wait_all<0>();
+}
+
 // General / exact path.  One CTA per (frame, strip of CF_W beams); thread = beam.
 template <typename InT>
 __global__ void __launch_bounds__(CF_W) cfar_exact_kernel(const InT *__restrict__ img, const CfarParams p,
@@ -414,6 +569,43 @@ static int launch_ring_alg(sfe_ctx *ctx, const CUtensorMap &in_map, const CUtens
   }
 }
 
+// M[S] = smallest uint8 cell value x with (double)x > tau*S/div (the reference's compare) and
+// (double)x > gate (the node's amplitude gate); 256 = no value passes.
+static void build_u8_lut(const CfarParams &p, std::vector<uint16_t> &lut) {
+  const int n = (p.alg == SFE_CFAR_CA ? 2 : 1) * CF_T * 255 + 1;
+  lut.resize(n);
+  int g = 0;
+  if (p.gate_on) {
+    if (p.gate_d != p.gate_d) g = 256;
+    else if (p.gate_d < 0) g = 0;
+    else if (p.gate_d >= 255.0) g = 256;
+    else g = (int)floor(p.gate_d) + 1;
+  }
+  for (int S = 0; S < n; ++S) {
+    const double d = p.tau * (double)(float)S / p.div;
+    int m;
+    if (d != d) m = 256;
+    else if (d < 0) m = 0;
+    else if (d >= 255.0) m = 256;
+    else m = (int)floor(d) + 1;
+    lut[S] = (uint16_t)(m > g ? m : g);
+  }
+}
+
+template <int ALG>
+static int launch_u8_lut(sfe_ctx *ctx, const CUtensorMap &in_map, const CUtensorMap &out_map, const CfarParams &p,
+                         const uint16_t *lut, int lut_n) {
+  const bool m = p.mask != nullptr, b = p.bits != nullptr;
+  const int grid = p.F * p.strips, thr = CF_W + 32;
+  if (m && b) cfar_u8_lut_kernel<ALG, true, true><<<grid, thr, 0, ctx->stream>>>(in_map, out_map, p, lut, lut_n);
+  else if (m) cfar_u8_lut_kernel<ALG, true, false><<<grid, thr, 0, ctx->stream>>>(in_map, out_map, p, lut, lut_n);
+  else if (b) cfar_u8_lut_kernel<ALG, false, true><<<grid, thr, 0, ctx->stream>>>(in_map, out_map, p, lut, lut_n);
+  else return SFE_OK;
+  SFE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SFE_OK;
+}
+
 template <typename InT>
 static int launch_exact(sfe_ctx *ctx, const InT *img, const CfarParams &p, const uint8_t *only_flagged) {
   size_t smem = 0;
@@ -489,6 +681,30 @@ int cfar_run(sfe_ctx *ctx, const void *img, int dtype, int F, int R, int B, int 
       rc = launch_ring_alg<float>(ctx, in_map, out_map, p);
       if (rc != SFE_OK) return rc;
       return launch_exact<float>(ctx, (const float *)img, p, p.flags);  // re-does flagged strips only
+    }
+    if (thr == nullptr && isfinite(tau)) {
+      // integer kernel with the threshold table (re-uploaded only when the parameters change)
+      static thread_local std::vector<uint16_t> lut_host;
+      static thread_local double key[5] = {-1, 0, 0, 0, 0};
+      static thread_local const void *key_buf = nullptr;
+      build_u8_lut(p, lut_host);
+      rc = ensure(ctx, ctx->scratch[SCR_CFAR_LUT], lut_host.size() * sizeof(uint16_t));
+      if (rc != SFE_OK) return rc;
+      const double k5[5] = {(double)alg, tau, (double)p.gate_on, p.gate_d, (double)lut_host.size()};
+      if (memcmp(k5, key, sizeof(key)) != 0 || key_buf != ctx->scratch[SCR_CFAR_LUT].ptr) {
+        SFE_CUDA(cudaMemcpyAsync(ctx->scratch[SCR_CFAR_LUT].ptr, lut_host.data(), lut_host.size() * sizeof(uint16_t),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        SFE_CUDA(cudaStreamSynchronize(ctx->stream));  // lut_host is reused by the next call
+        memcpy(key, k5, sizeof(key));
+        key_buf = ctx->scratch[SCR_CFAR_LUT].ptr;
+      }
+      const uint16_t *lut = (const uint16_t *)ctx->scratch[SCR_CFAR_LUT].ptr;
+      const int n = (int)lut_host.size();
+      switch (alg) {
+        case SFE_CFAR_CA: return launch_u8_lut<SFE_CFAR_CA>(ctx, in_map, out_map, p, lut, n);
+        case SFE_CFAR_SOCA: return launch_u8_lut<SFE_CFAR_SOCA>(ctx, in_map, out_map, p, lut, n);
+        default: return launch_u8_lut<SFE_CFAR_GOCA>(ctx, in_map, out_map, p, lut, n);
+      }
     }
     return launch_ring_alg<uint8_t>(ctx, in_map, out_map, p);
   }

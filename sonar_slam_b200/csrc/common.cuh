@@ -65,7 +65,7 @@ struct sfe_maps {  // per-geometry polar->Cartesian sampling table (featx.cu)
 };
 
 namespace sfe {
-enum { SCR_CFAR_FLAGS = 0, SCR_FEATX = 1, SCR_CLOUD = 2, SCR_ICP = 3, SCR_MISC = 4 };
+enum { SCR_CFAR_FLAGS = 0, SCR_FEATX = 1, SCR_CLOUD = 2, SCR_ICP = 3, SCR_MISC = 4, SCR_CFAR_LUT = 5 };
 
 int ensure(sfe_ctx *ctx, Buffer &b, size_t bytes);  // (re)allocate if too small
 int ensure_pinned(sfe_ctx *ctx, size_t bytes);
