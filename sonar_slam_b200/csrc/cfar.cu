@@ -448,7 +448,9 @@ __global__ void __launch_bounds__(CF_W + 32, 4)
     }
     fence_mbar_init();
   }
-  for (int i = tid; i < lut_n; i += CF_W + 32) lut[i] = lut_g[i];
+  // 16-byte copies (the device table is padded to a multiple of 8 entries)
+  for (int i = tid; i * 8 < lut_n; i += CF_W + 32)
+    reinterpret_cast<uint4 *>(lut)[i] = reinterpret_cast<const uint4 *>(lut_g)[i];
   __syncthreads();
 
   if (tid >= CF_W) {
@@ -688,6 +690,8 @@ int cfar_run(sfe_ctx *ctx, const void *img, int dtype, int F, int R, int B, int 
       static thread_local double key[5] = {-1, 0, 0, 0, 0};
       static thread_local const void *key_buf = nullptr;
       build_u8_lut(p, lut_host);
+      const int lut_n = (int)lut_host.size();
+      lut_host.resize((lut_host.size() + 7) / 8 * 8, 256);  // pad for the kernel's 16-byte copies
       rc = ensure(ctx, ctx->scratch[SCR_CFAR_LUT], lut_host.size() * sizeof(uint16_t));
       if (rc != SFE_OK) return rc;
       const double k5[5] = {(double)alg, tau, (double)p.gate_on, p.gate_d, (double)lut_host.size()};
@@ -699,7 +703,7 @@ int cfar_run(sfe_ctx *ctx, const void *img, int dtype, int F, int R, int B, int 
         key_buf = ctx->scratch[SCR_CFAR_LUT].ptr;
       }
       const uint16_t *lut = (const uint16_t *)ctx->scratch[SCR_CFAR_LUT].ptr;
-      const int n = (int)lut_host.size();
+      const int n = lut_n;
       switch (alg) {
         case SFE_CFAR_CA: return launch_u8_lut<SFE_CFAR_CA>(ctx, in_map, out_map, p, lut, n);
         case SFE_CFAR_SOCA: return launch_u8_lut<SFE_CFAR_SOCA>(ctx, in_map, out_map, p, lut, n);

@@ -142,21 +142,101 @@ __device__ __forceinline__ void grid_build(const float *__restrict__ src, int st
 
 struct NNResult {
   float d2;
-  int pos;  // sorted position, -1 if none
+  int pos;   // sorted position, -1 if none
+  int tie;   // another point at exactly the same distance was seen (resolved after the search)
 };
 
-// scan a contiguous range of sorted points
+// scan a contiguous range of sorted points (hot loop: no global memory, ties only flagged)
 __device__ __forceinline__ void nn_scan(const GridView &g, int s, int e, float qx, float qy, NNResult &r) {
   for (int p = s; p < e; ++p) {
     const float2 t = g.pts[p];
     const float d2 = dist2_rn(qx - t.x, qy - t.y);
+    r.tie |= (d2 == r.d2) & (p != r.pos);
     if (d2 < r.d2) {
       r.d2 = d2;
       r.pos = p;
-    } else if (d2 == r.d2 && r.pos >= 0 && g.orig != nullptr) {
-      if (g.orig[p] < g.orig[r.pos]) r.pos = p;  // tie: lowest original index
+      r.tie = 0;
     }
   }
+}
+
+// rare: among the points of the (2k+1)^2 block at exactly distance r.d2, keep the lowest original index
+static __device__ __noinline__ void nn_resolve_tie(const GridView &g, int cx, int cy, int k, float qx, float qy, NNResult &r) {
+  if (g.orig == nullptr || r.pos < 0) return;
+  const int xa = max(cx - k, 0), xb = min(cx + k, g.nx - 1);
+  int best = r.pos;
+  for (int y = max(cy - k, 0); y <= min(cy + k, g.ny - 1); ++y)
+    for (int p = g.cstart[y * g.nx + xa]; p < g.cstart[y * g.nx + xb + 1]; ++p) {
+      const float2 t = g.pts[p];
+      if (dist2_rn(qx - t.x, qy - t.y) == r.d2 && g.orig[p] < g.orig[best]) best = p;
+    }
+  r.pos = best;
+  r.tie = 0;
+}
+
+// conservative lower bound (squared) on the distance from the query to anything outside the
+// (2k+1)^2 block of cells around cell (cx, cy); +inf when the block covers the whole grid
+__device__ __forceinline__ float nn_block_bound2(const GridView &g, float qx, float qy, int cx, int cy, int k) {
+  const int x0 = cx - k, x1 = cx + k, y0 = cy - k, y1 = cy + k;
+  float bound = INFINITY;
+  if (x0 > 0) bound = fminf(bound, qx - (g.ox + (float)x0 * g.cell));
+  if (x1 < g.nx - 1) bound = fminf(bound, (g.ox + (float)(x1 + 1) * g.cell) - qx);
+  if (y0 > 0) bound = fminf(bound, qy - (g.oy + (float)y0 * g.cell));
+  if (y1 < g.ny - 1) bound = fminf(bound, (g.oy + (float)(y1 + 1) * g.cell) - qy);
+  if (bound == INFINITY) return INFINITY;
+  const float b = bound * (1.0f - 1e-5f) - 1e-6f;  // conservative against float rounding
+  return b > 0.f ? b * b * (1.0f - 1e-6f) : 0.f;
+}
+
+// scan the whole (2k+1)^2 block as one contiguous point range per cell row
+__device__ __forceinline__ void nn_scan_block(const GridView &g, int cx, int cy, int k, float qx, float qy, NNResult &r) {
+  const int xa = max(cx - k, 0), xb = min(cx + k, g.nx - 1);
+  for (int y = max(cy - k, 0); y <= min(cy + k, g.ny - 1); ++y)
+    nn_scan(g, g.cstart[y * g.nx + xa], g.cstart[y * g.nx + xb + 1], qx, qy, r);
+}
+
+// Continue a search that has already scanned the block of radius k_done (k_done = -1: nothing yet), until
+//   (a) the nearest neighbour is certain                      -> returns 1, r = exact NN (if any within max_d2)
+//   (b) every unscanned point is farther than sqrt(stop_d2)   -> returns 0, r = best so far (NOT exact); the
+//       caller only learns "the NN distance exceeds stop_d2"
+// The block of cells around the query doubles (k = 1, 2, 4, ...) while nothing has been found, each block
+// scanned as row spans (two offset loads per row), so a query far from every point costs O(k) cell
+// look-ups; once a candidate at distance d exists, one last block of radius ceil(d / cell) + 1 settles it.
+// Re-scanning inner cells is harmless (same candidates, same tie rule).
+__device__ __forceinline__ int nn_search(const GridView &g, float qx, float qy, float max_d2, float stop_d2,
+                                         int k_done, NNResult &r) {
+  if (g.n <= 0) return 1;
+  const int cx = grid_cell_coord(qx, g.ox, g.inv_cell, g.nx), cy = grid_cell_coord(qy, g.oy, g.inv_cell, g.ny);
+  const int kmax = max(g.nx, g.ny);
+  const float lim = fminf(max_d2, stop_d2);
+  int k = k_done;  // block radius scanned so far; -1 = nothing yet (start with the query's own cell, k = 0)
+  int exact = -1;
+  while (exact < 0) {
+    if (k >= 0) {
+      const float b2 = nn_block_bound2(g, qx, qy, cx, cy, k);
+      if (b2 == INFINITY || b2 > r.d2 || b2 > max_d2) {
+        exact = 1;  // nothing outside the block can beat the candidate / be accepted at all
+      } else if (b2 > stop_d2) {
+        exact = 0;  // NN is farther than the caller cares about
+      } else if (r.pos >= 0 && r.d2 <= lim) {
+        // a candidate the caller cares about: jump to the smallest block that contains every point at
+        // distance <= sqrt(d2) (its bound is re-checked at the top of the loop)
+        const float d = sqrtf(r.d2);
+        int kk = (int)(d * g.inv_cell * 1.0001f) + 1;
+        kk = min(max(kk, k + 1), kmax);
+        nn_scan_block(g, cx, cy, kk, qx, qy, r);
+        k = kk;
+        continue;
+      } else if (k >= kmax) {
+        exact = 1;
+      }
+      if (exact >= 0) break;
+    }
+    k = k < 0 ? 0 : (k == 0 ? 1 : min(2 * k, kmax));
+    nn_scan_block(g, cx, cy, k, qx, qy, r);
+  }
+  if (exact == 1 && r.tie) nn_resolve_tie(g, cx, cy, k, qx, qy, r);
+  return exact;
 }
 
 // exact nearest neighbour of (qx,qy); accepted only when d2 <= max_d2
@@ -164,38 +244,8 @@ __device__ __forceinline__ NNResult nn_query(const GridView &g, float qx, float 
   NNResult r;
   r.d2 = INFINITY;
   r.pos = -1;
-  if (g.n <= 0) return r;
-  const int cx = grid_cell_coord(qx, g.ox, g.inv_cell, g.nx), cy = grid_cell_coord(qy, g.oy, g.inv_cell, g.ny);
-  const int kmax = max(g.nx, g.ny);
-  for (int k = 1; k <= kmax; ++k) {
-    const int x0 = cx - k, x1 = cx + k, y0 = cy - k, y1 = cy + k;
-    const int xa = max(x0, 0), xb = min(x1, g.nx - 1);
-    if (k == 1) {  // the whole 3x3 block: three row spans
-      for (int y = max(y0, 0); y <= min(y1, g.ny - 1); ++y)
-        nn_scan(g, g.cstart[y * g.nx + xa], g.cstart[y * g.nx + xb + 1], qx, qy, r);
-    } else {       // ring k: two full rows + two single cells per inner row
-      if (y0 >= 0) nn_scan(g, g.cstart[y0 * g.nx + xa], g.cstart[y0 * g.nx + xb + 1], qx, qy, r);
-      if (y1 < g.ny) nn_scan(g, g.cstart[y1 * g.nx + xa], g.cstart[y1 * g.nx + xb + 1], qx, qy, r);
-      for (int y = max(y0 + 1, 0); y <= min(y1 - 1, g.ny - 1); ++y) {
-        if (x0 >= 0) nn_scan(g, g.cstart[y * g.nx + x0], g.cstart[y * g.nx + x0 + 1], qx, qy, r);
-        if (x1 < g.nx) nn_scan(g, g.cstart[y * g.nx + x1], g.cstart[y * g.nx + x1 + 1], qx, qy, r);
-      }
-    }
-    // every unvisited point lies outside the (2k+1)^2 block of cells around the query's cell
-    float bound = INFINITY;
-    if (x0 > 0) bound = fminf(bound, qx - (g.ox + (float)x0 * g.cell));
-    if (x1 < g.nx - 1) bound = fminf(bound, (g.ox + (float)(x1 + 1) * g.cell) - qx);
-    if (y0 > 0) bound = fminf(bound, qy - (g.oy + (float)y0 * g.cell));
-    if (y1 < g.ny - 1) bound = fminf(bound, (g.oy + (float)(y1 + 1) * g.cell) - qy);
-    if (bound == INFINITY) break;
-    if (bound > 0.f) {
-      const float b = bound * (1.0f - 1e-5f) - 1e-6f;  // conservative against float rounding
-      if (b > 0.f) {
-        const float b2 = b * b * (1.0f - 1e-6f);
-        if (b2 > r.d2 || b2 > max_d2) break;
-      }
-    }
-  }
+  r.tie = 0;
+  nn_search(g, qx, qy, max_d2, INFINITY, -1, r);
   if (r.pos >= 0 && !(r.d2 <= max_d2)) {
     r.pos = -1;
     r.d2 = INFINITY;

@@ -22,6 +22,9 @@ namespace sfe {
 
 constexpr int ICP_THREADS = 512;
 constexpr int ICP_HIST = 64;  // differential-checker history kept (>= smoothLength + 1)
+constexpr int ICP_COARSE = 8;            // fine cells per coarse cell edge
+constexpr int ICP_COARSE_WORDS = 96;     // bitmap words: cnx*cny <= 2048 + margin
+constexpr float ICP_PRUNED = 3.0e38f;    // "finite, but farther than we needed to know"
 
 enum { ICP_OK = 0, ICP_NO_OUTLIER = 1, ICP_NO_POINT = 2, ICP_NAN_ROT = 3, ICP_NAN_TRANS = 4, ICP_NOT_RIGID = 5,
        ICP_EMPTY_REF = 6, ICP_SKIPPED = 7, ICP_TOO_LARGE = 8 };
@@ -124,7 +127,52 @@ struct IcpShared {  // small fixed-size part of the shared state
   double red[8 * 32];
   float hq_w[ICP_HIST], hq_z[ICP_HIST], ht_x[ICP_HIST], ht_y[ICP_HIST];
   int hn;
+  int cnx, cny;               // coarse occupancy grid (ICP_COARSE x ICP_COARSE fine cells per coarse cell)
+  uint32_t coarse[ICP_COARSE_WORDS];
 };
+
+// k-th smallest (0-based) of the finite entries of vals[0..n): 4-pass radix select on the float bits
+// (non-negative floats order like their bit patterns).  All threads call it; kk < number of finite entries.
+__device__ __forceinline__ float block_select_kth(const float *vals, int n, int kk, IcpShared &sh) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  uint32_t prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int h = tid; h < 256; h += nthr) sh.hist[h] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) {
+      const float v = vals[i];
+      if (!(v < INFINITY)) continue;
+      const uint32_t u = __float_as_uint(v);
+      if ((u & mask) == prefix) atomicAdd(&sh.hist[(u >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {  // lane l owns bins 8l .. 8l+7
+      int c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c[j] = sh.hist[tid * 8 + j], sum += c[j];
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (tid >= d) incl += t;
+      }
+      int run = incl - sum;
+      if (kk >= run && kk < incl) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (kk >= run && kk < run + c[j]) sh.sel_bin = tid * 8 + j, sh.sel_k = kk - run;
+          run += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (uint32_t)sh.sel_bin << shift;
+    mask |= 255u << shift;
+    kk = sh.sel_k;
+  }
+  __syncthreads();
+  return __uint_as_float(prefix);
+}
 
 __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -141,6 +189,8 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
   float *dist = reinterpret_cast<float *>(smem_raw + off);
   off += sizeof(float) * (size_t)b.ns_max;
   uint16_t *match = reinterpret_cast<uint16_t *>(smem_raw + off);
+  off += sizeof(uint16_t) * (size_t)b.ns_max;
+  uint8_t *qstate = reinterpret_cast<uint8_t *>(smem_raw + off);
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   uint16_t *orig = b.orig_ws + (size_t)blockIdx.x * b.nt_max;
@@ -215,6 +265,28 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
     GridView g;
     grid_geometry(nt, sh.bbox[0], sh.bbox[1], sh.bbox[2], sh.bbox[3], 0.05f, g, b.max_cells);
     grid_build(tgt, 2, nt, mx, my, g, sorted, cells, orig, sh.scan);
+    // coarse occupancy: which 8x8 blocks of cells hold any point (answers "is anything within maxDist?"
+    // for far-away source points without walking the fine grid)
+    {
+      const int cnx = (g.nx + ICP_COARSE - 1) / ICP_COARSE, cny = (g.ny + ICP_COARSE - 1) / ICP_COARSE;
+      if (tid == 0) sh.cnx = cnx, sh.cny = cny;
+      for (int w = tid; w < ICP_COARSE_WORDS; w += nthr) sh.coarse[w] = 0;
+      __syncthreads();
+      if (cnx * cny <= ICP_COARSE_WORDS * 32) {
+        for (int cc = tid; cc < cnx * cny; cc += nthr) {
+          const int ccy = cc / cnx, ccx = cc - ccy * cnx;
+          bool occ = false;
+          for (int y = ccy * ICP_COARSE; y < min((ccy + 1) * ICP_COARSE, g.ny) && !occ; ++y) {
+            const int xa = ccx * ICP_COARSE, xb = min((ccx + 1) * ICP_COARSE, g.nx);
+            occ = g.cstart[y * g.nx + xb] > g.cstart[y * g.nx + xa];
+          }
+          if (occ) atomicOr(&sh.coarse[cc >> 5], 1u << (cc & 31));
+        }
+      } else if (tid == 0) {
+        sh.cnx = 0;  // too many coarse cells: the test is skipped
+      }
+      __syncthreads();
+    }
 
     // ---- 2. reading into the centred frame; T_iter = I; checker history
     if (tid == 0) {
@@ -237,18 +309,113 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
       float Ti[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) Ti[i] = sh.Ti[i];
-      // 3a. match
-      int my_fin = 0;
+      // 3a. match.  Exact nearest neighbours are only needed for the pairs that can get a non-zero weight:
+      //   pass A  every source point scans its 3x3 block of cells: that either settles its nearest neighbour
+      //           or at least yields a candidate, i.e. an UPPER bound on its NN distance;
+      //   pass B  points without a candidate inside maxDist learn whether ANY target point lies within
+      //           maxDist (they then count as "finite" in the trimmed quantile) -- from the coarse
+      //           occupancy grid when that is conclusive, else from a search that stops at the first hit;
+      //   pass C  with n_finite known, kk = floor(n_finite * ratio).  The kk-th smallest of the upper bounds
+      //           (maxDist^2 for a finite point without candidate) bounds the kk-th smallest true distance
+      //           from above: call it U.  An unsettled point whose search proves "farther than U" has weight
+      //           0 and needs no exact distance.  Results are identical to an exhaustive search (same
+      //           quantile element, same kept pairs); the far outliers of a scan stop costing O(area).
+      int n_fin = 0;
+      const float stop_a = (0.999f * g.cell) * (0.999f * g.cell);
       for (int i = tid; i < ns; i += nthr) {
         const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-        const NNResult r = nn_query(g, q.x, q.y, max_d2);
-        dist[i] = r.d2;
-        match[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
-        my_fin += r.pos >= 0;
+        NNResult r;
+        r.d2 = INFINITY, r.pos = -1, r.tie = 0;
+        const int exact = nn_search(g, q.x, q.y, max_d2, stop_a, -1, r);  // own cell, then at most the 3x3 block
+        const bool fin = r.pos >= 0 && r.d2 <= max_d2;
+        dist[i] = fin ? r.d2 : INFINITY;
+        match[i] = fin ? (uint16_t)r.pos : (uint16_t)0xffff;
+        qstate[i] = (exact ? 1 : 0) | (fin ? 2 : 0) | ((fin || exact) ? 4 : 0);  // settled / finite / known
+        n_fin += fin;
       }
-      // count finite matches (the scan's barriers also publish dist[] / match[])
+      // pass B: finiteness of the points that have no candidate yet
+      for (int i = tid; i < ns; i += nthr) {
+        if (qstate[i] & 4) continue;
+        const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+        int verdict = -1;  // 1 finite, 0 not, -1 unknown
+        if (sh.cnx > 0) {
+          const float C = g.cell * (float)ICP_COARSE, rad = prm.matcher_max_dist;
+          const int xa = max(0, (int)floorf((q.x - rad - g.ox) / C) - 1), xb = min(sh.cnx - 1, (int)floorf((q.x + rad - g.ox) / C) + 1);
+          const int ya = max(0, (int)floorf((q.y - rad - g.oy) / C) - 1), yb = min(sh.cny - 1, (int)floorf((q.y + rad - g.oy) / C) + 1);
+          if (xa > xb || ya > yb) {
+            verdict = 0;
+          } else if ((xb - xa + 1) * (yb - ya + 1) <= 256) {
+            const float r_in = rad * (1.f - 1e-4f) - g.cell * 1e-3f, r_out = rad * (1.f + 1e-4f) + g.cell * 1e-3f;
+            bool any_maybe = false;
+            for (int cy2 = ya; cy2 <= yb && verdict != 1; ++cy2)
+              for (int cx2 = xa; cx2 <= xb; ++cx2) {
+                const int cc = cy2 * sh.cnx + cx2;
+                if (!((sh.coarse[cc >> 5] >> (cc & 31)) & 1u)) continue;
+                const float x0 = g.ox + (float)cx2 * C, x1 = x0 + C, y0 = g.oy + (float)cy2 * C, y1 = y0 + C;
+                const float nx_ = fmaxf(fmaxf(x0 - q.x, q.x - x1), 0.f), ny_ = fmaxf(fmaxf(y0 - q.y, q.y - y1), 0.f);
+                const float fx_ = fmaxf(fabsf(x0 - q.x), fabsf(x1 - q.x)), fy_ = fmaxf(fabsf(y0 - q.y), fabsf(y1 - q.y));
+                if (fx_ * fx_ + fy_ * fy_ <= r_in * r_in) {
+                  verdict = 1;  // an occupied block lies entirely inside the acceptance disc
+                  break;
+                }
+                if (nx_ * nx_ + ny_ * ny_ <= r_out * r_out) any_maybe = true;
+              }
+            if (verdict != 1 && !any_maybe) verdict = 0;
+          }
+        }
+        if (verdict < 0) {  // inconclusive: grow the block until the first point inside maxDist shows up
+          NNResult r;
+          r.d2 = INFINITY, r.pos = -1, r.tie = 0;
+          const int cx = grid_cell_coord(q.x, g.ox, g.inv_cell, g.nx), cy = grid_cell_coord(q.y, g.oy, g.inv_cell, g.ny);
+          const int kmax = max(g.nx, g.ny);
+          verdict = 0;
+          for (int k = 2;; k = min(2 * k, kmax)) {
+            nn_scan_block(g, cx, cy, k, q.x, q.y, r);
+            if (r.d2 <= max_d2) {
+              verdict = 1;
+              break;
+            }
+            const float b2 = nn_block_bound2(g, q.x, q.y, cx, cy, k);
+            if (b2 == INFINITY || b2 > max_d2 || k >= kmax) break;
+          }
+        }
+        qstate[i] |= 4 | (verdict ? 2 : 0) | (verdict ? 0 : 1);  // "nothing within maxDist" is a settled answer
+        n_fin += verdict;
+        dist[i] = verdict ? max_d2 : INFINITY;  // upper bound of a finite point without candidate
+      }
       int total_fin;
-      block_exclusive_scan(my_fin, sh.scan, total_fin);
+      block_exclusive_scan(n_fin, sh.scan, total_fin);  // (its barriers also publish dist[] / qstate[])
+      // pass C: settle what still matters
+      {
+        float stop_d2 = INFINITY;
+        if (prm.trim_ratio >= 0.f) {
+          if (prm.trim_ratio < 1.0f && total_fin > 0) {
+            int kk = (int)(size_t)__fmul_rn((float)total_fin, prm.trim_ratio);
+            if (kk >= total_fin) kk = total_fin - 1;
+            stop_d2 = block_select_kth(dist, ns, kk, sh);  // kk-th smallest upper bound >= kk-th smallest distance
+          }
+        } else if (prm.outlier_max_dist > 0.f) {
+          stop_d2 = out_d2;
+        }
+        for (int i = tid; i < ns; i += nthr) {
+          if (qstate[i] & 1) continue;
+          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+          NNResult r;
+          r.pos = match[i] == 0xffff ? -1 : (int)match[i];
+          r.d2 = r.pos >= 0 ? dist[i] : INFINITY;
+          r.tie = 1;  // the candidate came from an earlier pass: re-check ties over the final block
+          const int exact = nn_search(g, q.x, q.y, max_d2, stop_d2, 1, r);
+          if (exact) {
+            const bool fin = r.pos >= 0 && r.d2 <= max_d2;  // == the finiteness found in pass B
+            dist[i] = fin ? r.d2 : INFINITY;
+            match[i] = fin ? (uint16_t)r.pos : (uint16_t)0xffff;
+          } else {
+            dist[i] = ICP_PRUNED;  // finite, farther than the quantile bound: weight 0
+            match[i] = 0xffff;
+          }
+        }
+      }
+      __syncthreads();
 
       // 3b. trimmed-distance limit = element floor(float(n)*ratio) of the ascending finite distances
       float limit = INFINITY;
@@ -261,7 +428,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         if (prm.trim_ratio == 1.0f) {
           float m = 0.f;
           for (int i = tid; i < ns; i += nthr)
-            if (match[i] != 0xffff) m = fmaxf(m, dist[i]);
+            if (dist[i] < INFINITY) m = fmaxf(m, dist[i]);
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
           float *fr = reinterpret_cast<float *>(sh.red);
@@ -274,41 +441,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         } else {
           int kk = (int)(size_t)__fmul_rn((float)total_fin, prm.trim_ratio);
           if (kk >= total_fin) kk = total_fin - 1;
-          uint32_t prefix = 0, mask = 0;
-          for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int h = tid; h < 256; h += nthr) sh.hist[h] = 0;
-            __syncthreads();
-            for (int i = tid; i < ns; i += nthr) {
-              if (match[i] == 0xffff) continue;
-              const uint32_t u = __float_as_uint(dist[i]);
-              if ((u & mask) == prefix) atomicAdd(&sh.hist[(u >> shift) & 255u], 1);
-            }
-            __syncthreads();
-            if (tid < 32) {  // lane l owns bins 8l .. 8l+7
-              int c[8], sum = 0;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) c[j] = sh.hist[tid * 8 + j], sum += c[j];
-              int incl = sum;
-#pragma unroll
-              for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (tid >= d) incl += t;
-              }
-              int run = incl - sum;
-              if (kk >= run && kk < incl) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (kk >= run && kk < run + c[j]) sh.sel_bin = tid * 8 + j, sh.sel_k = kk - run;
-                  run += c[j];
-                }
-              }
-            }
-            __syncthreads();
-            prefix |= (uint32_t)sh.sel_bin << shift;
-            mask |= 255u << shift;
-            kk = sh.sel_k;
-          }
-          limit = __uint_as_float(prefix);
+          limit = block_select_kth(dist, ns, kk, sh);
         }
       }
 
@@ -528,7 +661,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   b.prm = *prm;
   size_t smem = ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
                 sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
-                sizeof(float) * (size_t)b.ns_max + sizeof(uint16_t) * (size_t)b.ns_max + 16;
+                sizeof(float) * (size_t)b.ns_max + sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 16;
   if (smem > (size_t)ctx->max_smem_optin) {
     set_error("icp: source %d + target %d points need %zu B of shared memory per CTA (limit %d)", ns_max, nt_max, smem,
               ctx->max_smem_optin);
