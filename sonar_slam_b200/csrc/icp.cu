@@ -321,8 +321,18 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
       //           0 and needs no exact distance.  Results are identical to an exhaustive search (same
       //           quantile element, same kept pairs); the far outliers of a scan stop costing O(area).
       int n_fin = 0;
+      const bool small = ns <= 2 * nthr && nt <= 4096;  // few, cheap searches: one exact pass, no pruning
+      if (small) {
+        for (int i = tid; i < ns; i += nthr) {
+          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+          const NNResult r = nn_query(g, q.x, q.y, max_d2);
+          dist[i] = r.d2;
+          match[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
+          n_fin += r.pos >= 0;
+        }
+      }
       const float stop_a = (0.999f * g.cell) * (0.999f * g.cell);
-      for (int i = tid; i < ns; i += nthr) {
+      for (int i = tid; i < ns && !small; i += nthr) {
         const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
         NNResult r;
         r.d2 = INFINITY, r.pos = -1, r.tie = 0;
@@ -334,7 +344,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         n_fin += fin;
       }
       // pass B: finiteness of the points that have no candidate yet
-      for (int i = tid; i < ns; i += nthr) {
+      for (int i = tid; i < ns && !small; i += nthr) {
         if (qstate[i] & 4) continue;
         const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
         int verdict = -1;  // 1 finite, 0 not, -1 unknown
@@ -386,7 +396,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
       int total_fin;
       block_exclusive_scan(n_fin, sh.scan, total_fin);  // (its barriers also publish dist[] / qstate[])
       // pass C: settle what still matters
-      {
+      if (!small) {
         float stop_d2 = INFINITY;
         if (prm.trim_ratio >= 0.f) {
           if (prm.trim_ratio < 1.0f && total_fin > 0) {
