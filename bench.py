@@ -51,6 +51,21 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic_per_frame():
+    """dram read+write bytes per frame of the pipeline's CFAR kernel, from the committed ncu --set full
+    capture (profiles/r01_ncu_full_summaries.json, 4096-frame launch); None if absent."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r01_ncu_full_summaries.json")) as f:
+            d = json.load(f)["prof_cfar_u8lut"]
+
+        def gb(v):
+            x, unit = v.split()
+            return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return (gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])) / 4096.0
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -195,6 +210,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- this benchmark has no CPU fallback for the product path")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F, K, W = args.frames, args.steps, args.warmup
 
@@ -281,8 +297,9 @@ def run_ours(args):
             "e2e": {"value": world * F * K / e2e_s, "unit": "frames/s",
                     "h2d_bytes_per_step": F * R * B + F * 4 * 9 * 4, "d2h_bytes_per_step": F * (36 + 16)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "cfar_ring_tma_kernel<u8, SOCA, bits>", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "cfar_u8_lut_kernel<SOCA, bits>", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (ncu_traffic_per_frame() * F) if ncu_traffic_per_frame() else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": cfar_bytes,
                          "kernel_ms_per_launch": cfar_ms / max(1, cfar_calls)},
             "stage_share": {k: (v[0] / total_ms if total_ms else None) for k, v in stage.items()},

@@ -23,6 +23,8 @@ namespace sfe {
 
 constexpr int CLOUD_THREADS = 512;
 constexpr int DS_MAX_DEPTH = 15;
+constexpr int DS_FAST_DEPTH = 7;                 // 4^7 = 16384 leaves: counting-sort path
+constexpr int DS_FAST_CELLS = 1 << (2 * DS_FAST_DEPTH);
 
 struct CloudBatch {
   const float *pts;  // [total][dim]
@@ -38,6 +40,7 @@ struct CloudBatch {
   unsigned long long *sort_ws;  // global sort buffer when n_pad does not fit shared memory
   uint16_t *orig_ws;
   int sort_in_smem;
+  int fast_ok;  // shared memory was sized for the counting-sort path
 };
 
 __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBatch b) {
@@ -97,6 +100,104 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
     }
     __syncthreads();
     const int D = depth_s;
+    if (D <= DS_FAST_DEPTH && b.fast_ok) {
+      // ---- fast path: at most 4^7 leaves -> the path key indexes a table.  Counting sort by leaf (atomics;
+      //      members land in arbitrary order), then every leaf's members are put back in index order, which is
+      //      all the reference's member order is (a stable partition of the index list at every level).
+      uint16_t *key16 = reinterpret_cast<uint16_t *>(smem_raw);                                   // [n_max]
+      uint32_t *cellw = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(uint16_t) * (size_t)b.n_max + 15) & ~size_t(15)));
+      uint16_t *sidx = reinterpret_cast<uint16_t *>(cellw + DS_FAST_CELLS / 2 + 4);              // [n_max]
+      float *facc = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sidx) + ((sizeof(uint16_t) * (size_t)b.n_max + 15) & ~size_t(15)));
+      const int ncells = 1 << (2 * D), nwords = (ncells + 2) / 2;
+      for (int w = tid; w < nwords; w += nthr) cellw[w] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += nthr) {
+        const float x = pts[(size_t)i * b.dim], y = pts[(size_t)i * b.dim + 1];
+        float cx = geo[0], cy = geo[1], r = geo[2];
+        unsigned key = 0;
+        for (int d = 0; d < D; ++d) {
+          const unsigned id = (x > cx ? 1u : 0u) | (y > cy ? 2u : 0u);
+          key = (key << 2) | id;
+          r = __fmul_rn(r, 0.5f);
+          cx = __fadd_rn(cx, (id & 1u) ? r : -r);
+          cy = __fadd_rn(cy, (id & 2u) ? r : -r);
+        }
+        key16[i] = (uint16_t)key;
+        atomicAdd(&cellw[key >> 1], (key & 1u) ? 0x10000u : 1u);
+      }
+      __syncthreads();
+      {  // inclusive ends per leaf (two 16-bit counters per word)
+        const int per = (nwords + nthr - 1) / nthr;
+        const int w0 = min(tid * per, nwords), w1 = min(w0 + per, nwords);
+        int local = 0;
+        for (int w = w0; w < w1; ++w) local += (int)(cellw[w] & 0xffffu) + (int)(cellw[w] >> 16);
+        int total;
+        int run = block_exclusive_scan(local, scan, total);
+        for (int w = w0; w < w1; ++w) {
+          const uint32_t v = cellw[w];
+          const int lo = run + (int)(v & 0xffffu), hi = lo + (int)(v >> 16);
+          cellw[w] = (uint32_t)lo | ((uint32_t)hi << 16);
+          run = hi;
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += nthr) {
+        const unsigned key = key16[i];
+        const uint32_t old = atomicSub(&cellw[key >> 1], (key & 1u) ? 0x10000u : 1u);
+        sidx[(int)((key & 1u) ? (old >> 16) : (old & 0xffffu)) - 1] = (uint16_t)i;
+      }
+      __syncthreads();
+      const uint16_t *cstart = reinterpret_cast<const uint16_t *>(cellw);  // [ncells + 1], entry ncells == n
+      // members of every leaf back into index order (insertion sort; leaves are small)
+      for (int c = tid; c < ncells; c += nthr) {
+        const int s0 = cstart[c], e0 = cstart[c + 1];
+        for (int a = s0 + 1; a < e0; ++a) {
+          const uint16_t v = sidx[a];
+          int q = a - 1;
+          while (q >= s0 && sidx[q] > v) sidx[q + 1] = sidx[q], --q;
+          sidx[q + 1] = v;
+        }
+      }
+      __syncthreads();
+      // per member: float32 sum of distances to the members of its leaf, in member order
+      for (int a = tid; a < n; a += nthr) {
+        const int ia = sidx[a];
+        const unsigned key = key16[ia];
+        const int s0 = cstart[key], e0 = cstart[key + 1];
+        const float ax = pts[(size_t)ia * b.dim], ay = pts[(size_t)ia * b.dim + 1];
+        float sum = 0.f;
+        for (int q = s0; q < e0; ++q) {
+          const int iq = sidx[q];
+          sum = __fadd_rn(sum, sqrtf(dist2_rn(ax - pts[(size_t)iq * b.dim], ay - pts[(size_t)iq * b.dim + 1])));
+        }
+        facc[a] = sum;
+      }
+      __syncthreads();
+      // leaves in key order (= depth-first order): every thread owns a contiguous run of leaves
+      {
+        const int per = (ncells + nthr - 1) / nthr;
+        const int c0 = min(tid * per, ncells), c1 = min(c0 + per, ncells);
+        int mine = 0;
+        for (int c = c0; c < c1; ++c) mine += cstart[c + 1] > cstart[c];
+        int total;
+        int rank = block_exclusive_scan(mine, scan, total);
+        for (int c = c0; c < c1; ++c) {
+          const int s0 = cstart[c], e0 = cstart[c + 1];
+          if (e0 <= s0) continue;
+          float best = 3.402823466e+38f;
+          int med = s0;
+          for (int q = s0; q < e0; ++q)
+            if (facc[q] < best) best = facc[q], med = q;
+          const int idx = sidx[med];
+          const size_t dst = (size_t)(o + rank);
+          for (int d = 0; d < b.dim; ++d) b.out_pts[dst * b.dim + d] = pts[(size_t)idx * b.dim + d];
+          b.out_idx[dst] = idx;
+          ++rank;
+        }
+        if (tid == 0) b.out_count[cl] = total;
+      }
+      continue;
+    }
     int n_pad = 2;  // bitonic sort size for THIS cloud
     while (n_pad < n) n_pad <<= 1;
     // ---- path key of every point, then sort (key, index)
@@ -289,6 +390,12 @@ int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cn
   size_t smem_sort = sizeof(unsigned long long) * (size_t)b.n_pad, smem_acc = sizeof(float) * (size_t)b.n_max + 16;
   b.sort_in_smem = smem_sort + smem_acc <= (size_t)ctx->max_smem_optin - 4096;
   size_t smem = (b.sort_in_smem ? smem_sort : 0) + smem_acc;
+  {
+    const size_t a16 = (sizeof(uint16_t) * (size_t)b.n_max + 15) & ~size_t(15);
+    const size_t fast = a16 + sizeof(uint32_t) * (DS_FAST_CELLS / 2 + 4) + a16 + sizeof(float) * (size_t)b.n_max + 16;
+    b.fast_ok = b.n_max <= 65535 && fast <= (size_t)ctx->max_smem_optin - 4096;
+    if (b.fast_ok && fast > smem) smem = fast;
+  }
   if (smem > (size_t)ctx->max_smem_optin - 4096) {
     set_error("downsample: clouds of %d points are not supported (shared memory)", n_max);
     return SFE_ERR_UNSUPPORTED;

@@ -56,9 +56,9 @@ __global__ void fill_offsets_kernel(int32_t *off, int n, int stride) {
 // float32 transform of window slot w (frame i-window+w), rel[i][window] the ICP guess.  One CTA per frame.
 __global__ void __launch_bounds__(256)
     assemble_targets_kernel(const float *__restrict__ clouds, const int32_t *__restrict__ counts, int cap,
-                            const float *__restrict__ rel, int F, int window, float *__restrict__ tgt,
+                            const float *__restrict__ rel, int f0, int F, int window, float *__restrict__ tgt,
                             int32_t *__restrict__ tgt_count, int tgt_cap, float *__restrict__ guess) {
-  const int i = blockIdx.x;
+  const int i = f0 + blockIdx.x;  // frames [f0, F) of the batch
   if (i >= F) return;
   const float *myrel = rel + (size_t)i * (window + 1) * 9;
   if (threadIdx.x < 9) guess[9 * (size_t)i + threadIdx.x] = myrel[window * 9 + threadIdx.x];
@@ -321,30 +321,31 @@ static const float *fe_cloud(const sfe_frontend *fe, const int32_t **cnt) {
   return fe->xy_a;
 }
 
-// stage 4-5 on the whole batch: targets from the window of previous frames, then ICP
-static int fe_match(sfe_frontend *fe, int n) {
+// stage 4-5 on frames [f0, f0+n): targets from the window of previous frames (which may precede f0), then ICP
+static int fe_match(sfe_frontend *fe, int f0, int n) {
   sfe_ctx *ctx = fe->ctx;
   const sfe_frontend_params &p = fe->p;
   const int cap = p.cap_points, tcap = p.window * cap;
   const int32_t *cnt;
   const float *cloud = fe_cloud(fe, &cnt);
   fe_tic(fe, SFE_FE_SUBMAP);
-  assemble_targets_kernel<<<n, 256, 0, ctx->stream>>>(cloud, cnt, cap, fe->rel, n, p.window, fe->tgt_a, fe->tcnt_a,
-                                                      tcap, fe->guess);
+  assemble_targets_kernel<<<n, 256, 0, ctx->stream>>>(cloud, cnt, cap, fe->rel, f0, f0 + n, p.window, fe->tgt_a,
+                                                      fe->tcnt_a, tcap, fe->guess);
   SFE_CUDA(cudaGetLastError());
   ctx->launches++;
   const float *tgt = fe->tgt_a;
   const int32_t *tcnt = fe->tcnt_a;
   if (p.submap_resolution > 0.f) {
-    int rc = downsample_run(ctx, fe->tgt_a, fe->off_tgt, fe->tcnt_a, n, 2, tcap, p.submap_resolution, fe->tgt_b,
-                            fe->tgt_idx, fe->tcnt_b);
+    int rc = downsample_run(ctx, fe->tgt_a, fe->off_tgt + f0, fe->tcnt_a + f0, n, 2, tcap, p.submap_resolution,
+                            fe->tgt_b, fe->tgt_idx, fe->tcnt_b + f0);
     if (rc != SFE_OK) return rc;
     tgt = fe->tgt_b, tcnt = fe->tcnt_b;
   }
   fe_toc(fe);
   fe_tic(fe, SFE_FE_ICP);
-  int rc = icp_run(ctx, &p.icp, cloud, fe->off_pts, cnt, tgt, fe->off_tgt, tcnt, p.min_points, nullptr, nullptr, n,
-                   p.cap_source, p.cap_target, fe->guess, fe->T, fe->iters, fe->inliers, fe->status, fe->cnt_a, cap);
+  int rc = icp_run(ctx, &p.icp, cloud, fe->off_pts + f0, cnt + f0, tgt, fe->off_tgt + f0, tcnt + f0, p.min_points,
+                   nullptr, nullptr, n, p.cap_source, p.cap_target, fe->guess + 9 * (size_t)f0, fe->T + 9 * (size_t)f0,
+                   fe->iters + f0, fe->inliers + f0, fe->status + f0, fe->cnt_a + f0, cap);
   fe_toc(fe);
   return rc;
 }
@@ -388,7 +389,7 @@ int sfe_frontend_run_dev(sfe_frontend *fe, const uint8_t *frames_dev, const doub
   if (rc != SFE_OK) return rc;
   rc = fe_features(fe, frames_dev, 0, n_frames);
   if (rc != SFE_OK) return rc;
-  return fe_match(fe, n_frames);
+  return fe_match(fe, 0, n_frames);
 }
 
 int sfe_frontend_results_dev(const sfe_frontend *fe, const float **T, const int32_t **iters, const int32_t **inliers,
@@ -431,9 +432,10 @@ int sfe_frontend_run_host(sfe_frontend *fe, const uint8_t *frames_host, const do
     SFE_CUDA(cudaStreamWaitEvent(ctx->stream, fe->ev_copy[k & 1], 0));
     int rc = fe_features(fe, fe->frames + (size_t)f0 * fbytes, f0, n);
     if (rc != SFE_OK) return rc;
+    rc = fe_match(fe, f0, n);  // its window only reaches back into chunks already processed
+    if (rc != SFE_OK) return rc;
   }
-  int rc = fe_match(fe, n_frames);
-  if (rc != SFE_OK) return rc;
+  int rc = SFE_OK;
   SFE_CUDA(cudaMemcpyAsync(T_host, fe->T, sizeof(float) * 9 * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
   SFE_CUDA(cudaMemcpyAsync(iters_host, fe->iters, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
   SFE_CUDA(cudaMemcpyAsync(inliers_host, fe->inliers, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
