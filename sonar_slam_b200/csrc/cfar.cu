@@ -492,6 +492,64 @@ __global__ void __launch_bounds__(CF_W + 32, 4)
   if (MASK && tid == 0) tma_wait_all<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// OS-CFAR on uint8 images (cfar.cpp:76-96): the k-th smallest of the 2T training cells.  One thread per
+// beam marches down the range axis keeping a 256-bin histogram of its current training window (byte
+// counters, four per 32-bit word, word-interleaved over the 128 threads of the CTA so every access is
+// conflict free) and the running order statistic (value v, number of cells below it): moving one range bin
+// removes two cells and adds two, after which v moves by at most a few bins (Huang's sliding median,
+// generalised to rank k).  The double compare `x > tau * v` and the amplitude gate come from a 256-entry
+// table built on the host with the reference's expression.  Any train_hs <= 127 / guard_hs.
+__global__ void __launch_bounds__(CF_W) cfar_os_hist_kernel(const uint8_t *__restrict__ img, const CfarParams p,
+                                                            const uint16_t *__restrict__ lut_g) {
+  __shared__ uint32_t hs[64 * CF_W];
+  __shared__ uint16_t lut[256];
+  const int tid = threadIdx.x;
+  const int f = blockIdx.x / p.strips;
+  const int col0 = (blockIdx.x % p.strips) * CF_W;
+  const int col = col0 + tid;
+  const bool live = col < p.B;
+  const int R = p.R, B = p.B, T = p.T, G = p.G, half = T + G, k = p.k;
+  const uint8_t *colp = img + (size_t)f * R * B + (live ? col : 0);
+  for (int i = tid; i < 256; i += CF_W) lut[i] = lut_g[i];
+  for (int w = 0; w < 64; ++w) hs[w * CF_W + tid] = 0;
+  __syncthreads();
+  auto cnt = [&](int v) -> int { return (int)((hs[(v >> 2) * CF_W + tid] >> ((v & 3) * 8)) & 0xffu); };
+  auto bump = [&](int v, int up) {
+    const uint32_t d = 1u << ((v & 3) * 8);
+    if (up) hs[(v >> 2) * CF_W + tid] += d; else hs[(v >> 2) * CF_W + tid] -= d;
+  };
+  const int r_first = half, r_last = R - half - 1;  // rows with a full window
+  int v = 0, below = 0;
+  if (r_first <= r_last) {
+    for (int i = r_first - half; i <= r_first + half; ++i)
+      if (abs(i - r_first) > G) bump(colp[(size_t)i * B], 1);
+    while (below + cnt(v) <= k) below += cnt(v), ++v;
+  }
+  for (int r = 0; r < R; ++r) {
+    bool pass = false;
+    if (r >= r_first && r <= r_last) {
+      const int xc = colp[(size_t)r * B];
+      pass = live && xc >= (int)lut[v];
+      if (p.thr != nullptr && live) p.thr[((size_t)f * R + r) * B + col] = (float)(p.tau * (double)(float)v);
+      if (r < r_last) {  // slide the window to r + 1
+        const int a_out = colp[(size_t)(r - half) * B], a_in = colp[(size_t)(r - G) * B];
+        const int b_out = colp[(size_t)(r + G + 1) * B], b_in = colp[(size_t)(r + half + 1) * B];
+        bump(a_out, 0), bump(a_in, 1), bump(b_out, 0), bump(b_in, 1);
+        below += (a_in < v) + (b_in < v) - (a_out < v) - (b_out < v);
+        while (below > k) --v, below -= cnt(v);
+        while (below + cnt(v) <= k) below += cnt(v), ++v;
+      }
+    }
+    if (p.mask != nullptr && live) p.mask[((size_t)f * R + r) * B + col] = pass ? 1 : 0;
+    if (p.bits != nullptr) {
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      const int w = (col0 >> 5) + (tid >> 5);
+      if ((tid & 31) == 0 && w < p.words_per_row) p.bits[((size_t)f * R + r) * p.words_per_row + w] = bal;
+    }
+  }
+}
+
 // General / exact path.  One CTA per (frame, strip of CF_W beams); thread = beam.
 template <typename InT>
 __global__ void __launch_bounds__(CF_W) cfar_exact_kernel(const InT *__restrict__ img, const CfarParams p,
@@ -692,7 +750,7 @@ int cfar_run(sfe_ctx *ctx, const void *img, int dtype, int F, int R, int B, int 
       build_u8_lut(p, lut_host);
       const int lut_n = (int)lut_host.size();
       lut_host.resize((lut_host.size() + 7) / 8 * 8, 256);  // pad for the kernel's 16-byte copies
-      rc = ensure(ctx, ctx->scratch[SCR_CFAR_LUT], lut_host.size() * sizeof(uint16_t));
+      rc = ensure(ctx, ctx->scratch[SCR_CFAR_LUT], 65536);  // [0, 32 KiB): this table, [32 KiB, 64 KiB): the OS table
       if (rc != SFE_OK) return rc;
       const double k5[5] = {(double)alg, tau, (double)p.gate_on, p.gate_d, (double)lut_host.size()};
       if (memcmp(k5, key, sizeof(key)) != 0 || key_buf != ctx->scratch[SCR_CFAR_LUT].ptr) {
@@ -711,6 +769,26 @@ int cfar_run(sfe_ctx *ctx, const void *img, int dtype, int F, int R, int B, int 
       }
     }
     return launch_ring_alg<uint8_t>(ctx, in_map, out_map, p);
+  }
+  if (dtype == SFE_U8 && alg == SFE_CFAR_OS && !force_exact && T >= 1 && T <= 127 && R > 2 * (T + G) && isfinite(tau)) {
+    // sliding-histogram OS-CFAR; 256-entry pass table M[v] = smallest cell value with x > tau*v (and the gate)
+    std::vector<uint16_t> lut(256);
+    int g = 0;
+    if (p.gate_on) g = (p.gate_d != p.gate_d) ? 256 : (p.gate_d < 0 ? 0 : (p.gate_d >= 255.0 ? 256 : (int)floor(p.gate_d) + 1));
+    for (int v = 0; v < 256; ++v) {
+      const double d = tau * (double)(float)v;
+      const int m = (d != d) ? 256 : (d < 0 ? 0 : (d >= 255.0 ? 256 : (int)floor(d) + 1));
+      lut[v] = (uint16_t)(m > g ? m : g);
+    }
+    int rc = ensure(ctx, ctx->scratch[SCR_CFAR_LUT], 65536);
+    if (rc != SFE_OK) return rc;
+    uint16_t *lut_dev = (uint16_t *)((char *)ctx->scratch[SCR_CFAR_LUT].ptr + 32768);  // second half: OS table
+    SFE_CUDA(cudaMemcpyAsync(lut_dev, lut.data(), 512, cudaMemcpyHostToDevice, ctx->stream));
+    SFE_CUDA(cudaStreamSynchronize(ctx->stream));  // `lut` is a local
+    cfar_os_hist_kernel<<<F * p.strips, CF_W, 0, ctx->stream>>>((const uint8_t *)img, p, lut_dev);
+    SFE_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SFE_OK;
   }
   if (dtype == SFE_F32) return launch_exact<float>(ctx, (const float *)img, p, nullptr);
   return launch_exact<uint8_t>(ctx, (const uint8_t *)img, p, nullptr);

@@ -677,12 +677,18 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
               ctx->max_smem_optin);
     return SFE_ERR_UNSUPPORTED;
   }
-  SFE_CUDA(cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // CTA size follows the source size (one NN query per thread and iteration is the sweet spot)
   const int threads = b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS);
-  int per_sm = 1;
-  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, threads, smem));
-  if (per_sm < 1) per_sm = 1;
+  // the attribute / occupancy queries are cached per (smem, threads): the front end calls this per copy chunk
+  static thread_local size_t c_smem = 0;
+  static thread_local int c_threads = 0, c_per_sm = 0, c_dev = -1;
+  if (c_smem != smem || c_threads != threads || c_dev != ctx->device) {
+    SFE_CUDA(cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int q = 1;
+    SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, icp_kernel, threads, smem));
+    c_smem = smem, c_threads = threads, c_per_sm = q < 1 ? 1 : q, c_dev = ctx->device;
+  }
+  const int per_sm = c_per_sm;
   int grid = ctx->sm_count * per_sm;
   if (grid > P) grid = P;
   int rc = ensure(ctx, ctx->scratch[SCR_ICP], (size_t)grid * b.nt_max * sizeof(uint16_t));

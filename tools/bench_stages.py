@@ -2,8 +2,8 @@
 import sys, time
 import numpy as np
 import torch
-from oracle import featx_ref
 from sonar_slam_b200 import _lib, ops, synth
+from sonar_slam_b200.bruce_slam.feature_extraction import FeatureExtraction
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
@@ -30,7 +30,8 @@ for i in range(0, F, 256):
             r0 = int(torch.randint(30, 479, (1,)).item()); w = int(torch.randint(30, 111, (1,)).item()); b0 = int(torch.randint(0, 512 - w, (1,)).item())
             x[f, r0:r0 + 3, b0:b0 + w] += 90 + 110 * float(torch.rand(1).item())
     imgs[i:i + n] = torch.clamp(torch.round(x), 0, 255).to(torch.uint8)
-geo = featx_ref.Geometry(30.0 / 512, 512, synth.bearings_oculus(512))
+geo = FeatureExtraction()
+geo.generate_map_xy(synth.Ping(0, None, 30.0 / 512, 512, synth.bearings_oculus(512)))
 maps = _lib.Maps(ctx, geo.map_x, geo.map_y, 512, 512, geo.width, geo.height)
 TAU = 2.749063720096473
 t, det = timeit(lambda: ops.cfar(imgs, "SOCA", 20, 5, TAU, gate=65, want_mask=False, want_bits=True))
