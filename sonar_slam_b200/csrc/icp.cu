@@ -678,7 +678,8 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
     return SFE_ERR_UNSUPPORTED;
   }
   // CTA size follows the source size (one NN query per thread and iteration is the sweet spot)
-  const int threads = b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS);
+  int threads = b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS);
+  if (const char *e = getenv("SFE_ICP_THREADS")) threads = atoi(e);  // development knob
   // the attribute / occupancy queries are cached per (smem, threads): the front end calls this per copy chunk
   static thread_local size_t c_smem = 0;
   static thread_local int c_threads = 0, c_per_sm = 0, c_dev = -1;

@@ -101,7 +101,9 @@ struct sfe_frontend {
   float *tgt_a, *tgt_b; // [max_frames][window*cap][2]
   int32_t *tgt_idx, *tcnt_a, *tcnt_b;
   float *rel;           // [max_frames][window+1][9] relative transforms (window slots, then the guess)
-  float *rel_host;      // pinned staging of the same
+  float *rel_host[2];   // pinned staging of the same, double-buffered (no stream sync per call)
+  cudaEvent_t ev_rel[2];
+  int rel_turn;
   float *guess, *T;
   int32_t *iters, *inliers, *status;
   cudaStream_t copy_stream;
@@ -195,11 +197,13 @@ int sfe_frontend_create(sfe_ctx *ctx, const sfe_maps *maps, const sfe_frontend_p
   FE_ALLOC(fe->tcnt_a, F * 4);
   FE_ALLOC(fe->tcnt_b, F * 4);
   FE_ALLOC(fe->rel, F * (params->window + 1) * 9 * 4);
-  if (cudaMallocHost((void **)&fe->rel_host, F * (params->window + 1) * 9 * 4) != cudaSuccess) {
-    sfe::set_error("sfe_frontend_create: cudaMallocHost failed");
-    sfe_frontend_destroy(fe);
-    return SFE_ERR_CUDA;
-  }
+  for (int k = 0; k < 2; ++k)
+    if (cudaMallocHost((void **)&fe->rel_host[k], F * (params->window + 1) * 9 * 4) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_rel[k], cudaEventDisableTiming) != cudaSuccess) {
+      sfe::set_error("sfe_frontend_create: pinned staging allocation failed");
+      sfe_frontend_destroy(fe);
+      return SFE_ERR_CUDA;
+    }
   FE_ALLOC(fe->guess, F * 9 * 4);
   FE_ALLOC(fe->T, F * 9 * 4);
   FE_ALLOC(fe->iters, F * 4);
@@ -231,7 +235,10 @@ void sfe_frontend_destroy(sfe_frontend *fe) {
                   fe->guess, fe->T, fe->iters, fe->inliers, fe->status};
   for (void *b : bufs)
     if (b) cudaFree(b);
-  if (fe->rel_host) cudaFreeHost(fe->rel_host);
+  for (int k = 0; k < 2; ++k) {
+    if (fe->rel_host[k]) cudaFreeHost(fe->rel_host[k]);
+    if (fe->ev_rel[k]) cudaEventDestroy(fe->ev_rel[k]);
+  }
   if (fe->copy_stream) cudaStreamDestroy(fe->copy_stream);
   for (auto &ev : fe->ev_copy)
     if (ev) cudaEventDestroy(ev);
@@ -247,9 +254,11 @@ void sfe_frontend_destroy(sfe_frontend *fe) {
 // window transforms + guesses from the odometry poses (host, double), uploaded as float32
 static int fe_upload_poses(sfe_frontend *fe, const double *poses, int n) {
   const int W = fe->p.window;
-  SFE_CUDA(cudaStreamSynchronize(fe->ctx->stream));  // rel_host may still be in flight from the previous call
+  const int turn = fe->rel_turn ^= 1;
+  SFE_CUDA(cudaEventSynchronize(fe->ev_rel[turn]));  // the copy that last used this staging buffer (two calls ago)
+  float *stage = fe->rel_host[turn];
   for (int i = 0; i < n; ++i) {
-    float *r = fe->rel_host + (size_t)i * (W + 1) * 9;
+    float *r = stage + (size_t)i * (W + 1) * 9;
     for (int w = 0; w < W; ++w) {
       const int k = i - W + w;
       if (k >= 0 && i > 0)
@@ -262,8 +271,9 @@ static int fe_upload_poses(sfe_frontend *fe, const double *poses, int n) {
     else
       for (int q = 0; q < 9; ++q) r[W * 9 + q] = (q % 4 == 0) ? 1.f : 0.f;
   }
-  SFE_CUDA(cudaMemcpyAsync(fe->rel, fe->rel_host, sizeof(float) * 9 * (size_t)n * (W + 1), cudaMemcpyHostToDevice,
+  SFE_CUDA(cudaMemcpyAsync(fe->rel, stage, sizeof(float) * 9 * (size_t)n * (W + 1), cudaMemcpyHostToDevice,
                            fe->ctx->stream));
+  SFE_CUDA(cudaEventRecord(fe->ev_rel[turn], fe->ctx->stream));
   return SFE_OK;
 }
 
