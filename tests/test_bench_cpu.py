@@ -1,0 +1,39 @@
+"""CPU-only: the CPU legs of bench.py (cpu_baseline / --impl reference) run and speak the JSON contract."""
+import json
+import subprocess
+import sys
+
+import numpy as np
+
+
+def test_cpu_pipeline_leg_runs_on_a_tiny_sample():
+    import bench
+    from sonar_slam_b200 import synth
+    d = synth.make_trajectory_frames(6, seed=1)
+    bench._cpu_init(d["bearings"])
+    secs = bench.cpu_pipeline(d["frames"].numpy(), d["poses_odom"], d["bearings"])
+    assert 0.0 < secs < 60.0
+
+
+def test_reference_arm_prints_one_json_line(monkeypatch, capsys):
+    import bench
+    monkeypatch.setattr(bench.os, "cpu_count", lambda: 2)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"])
+    a = bench.parse()
+    bench.run_reference(a)
+    out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(out) == 1
+    line = json.loads(out[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["cores"] == 2 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_refuses_to_run_the_product_path_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "0"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
