@@ -65,9 +65,9 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums /* [33
 
 // Choose grid geometry for n points with bounding box [minx,maxx] x [miny,maxy].
 __device__ __forceinline__ void grid_geometry(int n, float minx, float miny, float maxx, float maxy, float min_cell,
-                                              GridView &g, int max_cells) {
+                                              GridView &g, int max_cells, float cell_scale = 1.0f) {
   const float w = maxx - minx, h = maxy - miny;
-  float cell = sqrtf((w * h) / (float)(n > 0 ? n : 1));
+  float cell = cell_scale * sqrtf((w * h) / (float)(n > 0 ? n : 1));
   if (!(cell > min_cell)) cell = min_cell;
   if (!(cell > 1e-6f)) cell = 1.f;
   // keep the cell table within max_cells (<= GRID_MAX_CELLS)

@@ -45,6 +45,7 @@ struct IcpBatch {
   float *T_out;       // [P][9]
   int *iters, *inliers, *status;
   int P, ns_max, nt_max, max_cells;
+  float cell_scale;  // grid cell = cell_scale * sqrt(area / n)
   sfe_icp_params prm;
   uint16_t *orig_ws;  // [gridDim.x][nt_max]
 };
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
     }
     const float mx = sh.mean[0], my = sh.mean[1];
     GridView g;
-    grid_geometry(nt, sh.bbox[0], sh.bbox[1], sh.bbox[2], sh.bbox[3], 0.05f, g, b.max_cells);
+    grid_geometry(nt, sh.bbox[0], sh.bbox[1], sh.bbox[2], sh.bbox[3], 0.05f, g, b.max_cells, b.cell_scale);
     grid_build(tgt, 2, nt, mx, my, g, sorted, cells, orig, sh.scan);
     // coarse occupancy: which 8x8 blocks of cells hold any point (answers "is anything within maxDist?"
     // for far-away source points without walking the fine grid)
@@ -668,6 +669,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   b.T_out = T_out, b.iters = iters, b.inliers = inliers, b.status = status;
   b.P = P, b.ns_max = ns_max > 0 ? ns_max : 1, b.nt_max = nt_max > 0 ? nt_max : 1;
   b.max_cells = pick_max_cells(b.nt_max);
+  b.cell_scale = 1.0f;
   b.prm = *prm;
   size_t smem = ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
                 sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
@@ -678,8 +680,8 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
     return SFE_ERR_UNSUPPORTED;
   }
   // CTA size follows the source size (one NN query per thread and iteration is the sweet spot)
-  int threads = b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS);
-  if (const char *e = getenv("SFE_ICP_THREADS")) threads = atoi(e);  // development knob
+  // (measured on the config-4 replay: 256 threads beat 128 and 512 for ~360-point sources)
+  const int threads = b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS);
   // the attribute / occupancy queries are cached per (smem, threads): the front end calls this per copy chunk
   static thread_local size_t c_smem = 0;
   static thread_local int c_threads = 0, c_per_sm = 0, c_dev = -1;
