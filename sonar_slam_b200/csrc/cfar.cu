@@ -139,6 +139,21 @@ __device__ __noinline__ void cfar_resolve_block(const CfarParams &p, uint8_t (*o
   *pass_bits = pb;
 }
 
+// Input ring without a producer warp.  Every 16-row block reads its two TMA boxes into registers up
+// front and ends with a CTA-wide barrier, so after the barrier of block `blk` box blk-1 is dead and its
+// stage can take box blk + CF_NSTAGE - 1: one thread re-arms the stage's mbarrier and issues the load.
+template <typename InT>
+__device__ __forceinline__ void cfar_refill(InT (*tile)[CF_CH][CF_W], uint64_t *full_bar, const CUtensorMap *in_map,
+                                            const int blk, const int nchunks, const int tid, const int f,
+                                            const int col0) {
+  const int c = blk + CF_NSTAGE - 1;
+  if (tid == 0 && c < nchunks) {
+    const int st = c & (CF_NSTAGE - 1);
+    mbar_arrive_expect_tx(&full_bar[st], CF_CH * CF_W * (int)sizeof(InT));
+    tma_load_3d(&tile[st][0][0], in_map, &full_bar[st], col0, c * CF_CH, f);
+  }
+}
+
 struct CfarStep {  // per-thread streaming state (all in registers; indices are static after unrolling)
   float xr[CF_RING];  // x[rn - a]      at slot (J - a) & 31
   float wr[CF_RING];  // W[rn - a] = sum of the 20 cells ending at rn - a
@@ -201,7 +216,7 @@ __device__ __forceinline__ void cfar_step(CfarStep &s, const float xn, uint8_t (
 template <typename InT, int ALG, bool WITH_THR, bool MASK, bool BITS, bool EDGE, int Q>
 __device__ __forceinline__ void cfar_block16(CfarStep &s, InT (*tile)[CF_CH][CF_W], uint8_t (*obuf)[CF_CH][CF_W],
                                              uint32_t (*obits)[CF_CH][CF_W / 32], uint64_t *full_bar,
-                                             uint64_t *empty_bar, const CfarParams &p, const int blk,
+                                             const CUtensorMap *in_map, const CfarParams &p, const int blk,
                                              const int nchunks, const int tid, const int f, const int col0,
                                              const float c_hi, const float c_lo, const float gate) {
   const int r0 = (blk - 2) * CF_CH;
@@ -224,17 +239,17 @@ __device__ __forceinline__ void cfar_block16(CfarStep &s, InT (*tile)[CF_CH][CF_
 #pragma unroll
   for (int i = CF_SPLIT; i < CF_CH; ++i)  // row i - 7 of box blk
     xin[i] = (!EDGE || hasB) ? cell_to_float(tileB[i - CF_SPLIT][tid]) : 0.f;
-  if (hasA) {  // box blk-1 fully consumed by this warp
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty_bar[cA & (CF_NSTAGE - 1)]);
-  }
 #define SFE_STEP(I)                                                                                          \
   cfar_step<InT, ALG, WITH_THR, MASK, BITS, EDGE, Q * CF_CH + I>(s, xin[I], obuf[ob], p, r0 + I, tid, f, col, \
                                                                  c_hi, c_lo, gate, amb, pass_bits);
   SFE_STEP(0) SFE_STEP(1) SFE_STEP(2) SFE_STEP(3) SFE_STEP(4) SFE_STEP(5) SFE_STEP(6) SFE_STEP(7)
   SFE_STEP(8) SFE_STEP(9) SFE_STEP(10) SFE_STEP(11) SFE_STEP(12) SFE_STEP(13) SFE_STEP(14) SFE_STEP(15)
 #undef SFE_STEP
-  if (EDGE && r0 < 0) return;  // priming blocks: no output rows
+  if (EDGE && r0 < 0) {  // priming blocks: no output rows
+    named_bar_sync(1, CF_W);
+    cfar_refill<InT>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
+    return;
+  }
   if (!WITH_THR && amb) {
     uint32_t fixed = 0;
     cfar_resolve_block<InT>(p, MASK ? obuf[ob] : nullptr, &fixed, f, col, r0, tid);
@@ -252,6 +267,7 @@ __device__ __forceinline__ void cfar_block16(CfarStep &s, InT (*tile)[CF_CH][CF_
   if (MASK) fence_proxy_async_smem();
   if (MASK && tid == 0) tma_wait_read<0>();  // the other buffer's TMA store has finished reading it
   named_bar_sync(1, CF_W);
+  cfar_refill<InT>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
   if (MASK && tid == 0) {
     tma_store_3d(p.out_map, &obuf[ob][0][0], col0, r0, f);
     tma_commit();
@@ -265,14 +281,13 @@ __device__ __forceinline__ void cfar_block16(CfarStep &s, InT (*tile)[CF_CH][CF_
 }
 
 template <typename InT, int ALG, bool WITH_THR, bool MASK, bool BITS>
-__global__ void __launch_bounds__(CF_W + 32, 3)
+__global__ void __launch_bounds__(CF_W, 4)
     cfar_ring_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                          CfarParams p) {
   __shared__ __align__(128) InT tile[CF_NSTAGE][CF_CH][CF_W];
   __shared__ __align__(128) uint8_t obuf[2][CF_CH][CF_W];
   __shared__ uint32_t obits[2][CF_CH][CF_W / 32];
   __shared__ __align__(8) uint64_t full_bar[CF_NSTAGE];
-  __shared__ __align__(8) uint64_t empty_bar[CF_NSTAGE];
 
   const int tid = threadIdx.x;
   const int f = blockIdx.x / p.strips;
@@ -282,29 +297,17 @@ __global__ void __launch_bounds__(CF_W + 32, 3)
   const int nchunks = (R + CF_CH - 1) / CF_CH;
 
   if (tid == 0) {
-    for (int s = 0; s < CF_NSTAGE; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CF_W / 32);
-    }
+    prefetch_tmap(&in_map);
+    for (int s = 0; s < CF_NSTAGE; ++s) mbar_init(&full_bar[s], 1);
     fence_mbar_init();
+    for (int c = 0; c < CF_NSTAGE - 1 && c < nchunks; ++c) {  // the ring is refilled block by block (cfar_refill)
+      mbar_arrive_expect_tx(&full_bar[c], CF_CH * CF_W * (int)sizeof(InT));
+      tma_load_3d(&tile[c][0][0], &in_map, &full_bar[c], col0, c * CF_CH, f);
+    }
   }
   __syncthreads();
 
-  if (tid >= CF_W) {
-    // ------------------------------------------------------------ producer warp
-    if (tid == CF_W) {
-      prefetch_tmap(&in_map);
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = c % CF_NSTAGE, it = c / CF_NSTAGE;
-        if (it > 0) mbar_wait(&empty_bar[st], (it - 1) & 1);
-        mbar_arrive_expect_tx(&full_bar[st], CF_CH * CF_W * (int)sizeof(InT));
-        tma_load_3d(&tile[st][0][0], &in_map, &full_bar[st], col0, c * CF_CH, f);
-      }
-    }
-    return;
-  }
-
-  // -------------------------------------------------------------- consumers (one beam each)
+  // one beam per thread
   CfarStep s;
 #pragma unroll
   for (int i = 0; i < CF_RING; ++i) s.xr[i] = 0.f, s.wr[i] = 0.f;
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(CF_W + 32, 3)
         const int r0 = (blk - 2) * CF_CH;
         const bool interior = (r0 >= CF_HALF) && (r0 + CF_CH - 1 < R - CF_HALF);  // implies both boxes exist
 #define SFE_BLOCK(EDGE_, Q_)                                                                                       \
-  cfar_block16<InT, ALG, WITH_THR, MASK, BITS, EDGE_, Q_>(s, tile, obuf, obits, full_bar, empty_bar, p, blk, nchunks, \
+  cfar_block16<InT, ALG, WITH_THR, MASK, BITS, EDGE_, Q_>(s, tile, obuf, obits, full_bar, &in_map, p, blk, nchunks, \
                                                           tid, f, col0, c_hi, c_lo, gate)
         if (interior) {
           if (q == 0) SFE_BLOCK(false, 0); else SFE_BLOCK(false, 1);
@@ -379,7 +382,7 @@ __device__ __forceinline__ void cfar_step_u8(CfarStepI &s, const int xn, uint8_t
 template <int ALG, bool MASK, bool BITS, bool EDGE, int Q>
 __device__ __forceinline__ void cfar_block16_u8(CfarStepI &s, uint8_t (*tile)[CF_CH][CF_W],
                                                 uint8_t (*obuf)[CF_CH][CF_W], uint32_t (*obits)[CF_CH][CF_W / 32],
-                                                uint64_t *full_bar, uint64_t *empty_bar, const uint16_t *lut,
+                                                uint64_t *full_bar, const CUtensorMap *in_map, const uint16_t *lut,
                                                 const CfarParams &p, const int blk, const int nchunks,
                                                 const int tid, const int f, const int col0) {
   const int r0 = (blk - 2) * CF_CH;
@@ -397,20 +400,21 @@ __device__ __forceinline__ void cfar_block16_u8(CfarStepI &s, uint8_t (*tile)[CF
   if (hasB) mbar_wait(&full_bar[cB & (CF_NSTAGE - 1)], (cB / CF_NSTAGE) & 1);
 #pragma unroll
   for (int i = CF_SPLIT; i < CF_CH; ++i) xin[i] = (!EDGE || hasB) ? (int)tileB[i - CF_SPLIT][tid] : 0;
-  if (hasA) {
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty_bar[cA & (CF_NSTAGE - 1)]);
-  }
 #define SFE_STEP(I) \
   cfar_step_u8<ALG, MASK, BITS, EDGE, Q * CF_CH + I>(s, xin[I], obuf[ob], lut, p.R, r0 + I, tid, col_ok, keep_bits);
   SFE_STEP(0) SFE_STEP(1) SFE_STEP(2) SFE_STEP(3) SFE_STEP(4) SFE_STEP(5) SFE_STEP(6) SFE_STEP(7)
   SFE_STEP(8) SFE_STEP(9) SFE_STEP(10) SFE_STEP(11) SFE_STEP(12) SFE_STEP(13) SFE_STEP(14) SFE_STEP(15)
 #undef SFE_STEP
-  if (EDGE && r0 < 0) return;
+  if (EDGE && r0 < 0) {
+    named_bar_sync(1, CF_W);
+    cfar_refill<uint8_t>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
+    return;
+  }
   if (BITS && (tid & 31) < CF_CH) obits[ob][tid & 31][tid >> 5] = keep_bits;
   if (MASK) fence_proxy_async_smem();
   if (MASK && tid == 0) tma_wait_read<0>();
   named_bar_sync(1, CF_W);
+  cfar_refill<uint8_t>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
   if (MASK && tid == 0) {
     tma_store_3d(p.out_map, &obuf[ob][0][0], col0, r0, f);
     tma_commit();
@@ -424,14 +428,13 @@ __device__ __forceinline__ void cfar_block16_u8(CfarStepI &s, uint8_t (*tile)[CF
 }
 
 template <int ALG, bool MASK, bool BITS>
-__global__ void __launch_bounds__(CF_W + 32, 4)
+__global__ void __launch_bounds__(CF_W, 5)
     cfar_u8_lut_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                        CfarParams p, const uint16_t *__restrict__ lut_g, const int lut_n) {
   __shared__ __align__(128) uint8_t tile[CF_NSTAGE][CF_CH][CF_W];
   __shared__ __align__(128) uint8_t obuf[2][CF_CH][CF_W];
   __shared__ uint32_t obits[2][CF_CH][CF_W / 32];
   __shared__ __align__(8) uint64_t full_bar[CF_NSTAGE];
-  __shared__ __align__(8) uint64_t empty_bar[CF_NSTAGE];
   __shared__ __align__(16) uint16_t lut[(ALG == SFE_CFAR_CA ? CF_LUT_MAX : CF_T * 255 + 1) + 7];
 
   const int tid = threadIdx.x;
@@ -442,29 +445,18 @@ __global__ void __launch_bounds__(CF_W + 32, 4)
   const int nchunks = (R + CF_CH - 1) / CF_CH;
 
   if (tid == 0) {
-    for (int st = 0; st < CF_NSTAGE; ++st) {
-      mbar_init(&full_bar[st], 1);
-      mbar_init(&empty_bar[st], CF_W / 32);
-    }
+    prefetch_tmap(&in_map);
+    for (int st = 0; st < CF_NSTAGE; ++st) mbar_init(&full_bar[st], 1);
     fence_mbar_init();
+    for (int c = 0; c < CF_NSTAGE - 1 && c < nchunks; ++c) {
+      mbar_arrive_expect_tx(&full_bar[c], CF_CH * CF_W);
+      tma_load_3d(&tile[c][0][0], &in_map, &full_bar[c], col0, c * CF_CH, f);
+    }
   }
   // 16-byte copies (the device table is padded to a multiple of 8 entries)
-  for (int i = tid; i * 8 < lut_n; i += CF_W + 32)
+  for (int i = tid; i * 8 < lut_n; i += CF_W)
     reinterpret_cast<uint4 *>(lut)[i] = reinterpret_cast<const uint4 *>(lut_g)[i];
   __syncthreads();
-
-  if (tid >= CF_W) {
-    if (tid == CF_W) {
-      prefetch_tmap(&in_map);
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = c % CF_NSTAGE, it = c / CF_NSTAGE;
-        if (it > 0) mbar_wait(&empty_bar[st], (it - 1) & 1);
-        mbar_arrive_expect_tx(&full_bar[st], CF_CH * CF_W);
-        tma_load_3d(&tile[st][0][0], &in_map, &full_bar[st], col0, c * CF_CH, f);
-      }
-    }
-    return;
-  }
 
   CfarStepI s;
 #pragma unroll
@@ -479,7 +471,7 @@ __global__ void __launch_bounds__(CF_W + 32, 4)
         const int r0 = (blk - 2) * CF_CH;
         const bool interior = (r0 >= CF_HALF) && (r0 + CF_CH - 1 < R - CF_HALF);
 #define SFE_BLOCK(EDGE_, Q_) \
-  cfar_block16_u8<ALG, MASK, BITS, EDGE_, Q_>(s, tile, obuf, obits, full_bar, empty_bar, lut, p, blk, nchunks, tid, f, col0)
+  cfar_block16_u8<ALG, MASK, BITS, EDGE_, Q_>(s, tile, obuf, obits, full_bar, &in_map, lut, p, blk, nchunks, tid, f, col0)
         if (interior) {
           if (q == 0) SFE_BLOCK(false, 0); else SFE_BLOCK(false, 1);
         } else {
@@ -596,7 +588,7 @@ static float gate_as_float(double t) {
 template <typename InT, int ALG, bool WITH_THR, bool MASK, bool BITS>
 static int launch_ring(sfe_ctx *ctx, const CUtensorMap &in_map, const CUtensorMap &out_map, const CfarParams &p) {
   cfar_ring_tma_kernel<InT, ALG, WITH_THR, MASK, BITS>
-      <<<p.F * p.strips, CF_W + 32, 0, ctx->stream>>>(in_map, out_map, p);
+      <<<p.F * p.strips, CF_W, 0, ctx->stream>>>(in_map, out_map, p);
   SFE_CUDA(cudaGetLastError());
   ctx->launches++;
   return SFE_OK;
@@ -656,7 +648,7 @@ template <int ALG>
 static int launch_u8_lut(sfe_ctx *ctx, const CUtensorMap &in_map, const CUtensorMap &out_map, const CfarParams &p,
                          const uint16_t *lut, int lut_n) {
   const bool m = p.mask != nullptr, b = p.bits != nullptr;
-  const int grid = p.F * p.strips, thr = CF_W + 32;
+  const int grid = p.F * p.strips, thr = CF_W;
   if (m && b) cfar_u8_lut_kernel<ALG, true, true><<<grid, thr, 0, ctx->stream>>>(in_map, out_map, p, lut, lut_n);
   else if (m) cfar_u8_lut_kernel<ALG, true, false><<<grid, thr, 0, ctx->stream>>>(in_map, out_map, p, lut, lut_n);
   else if (b) cfar_u8_lut_kernel<ALG, false, true><<<grid, thr, 0, ctx->stream>>>(in_map, out_map, p, lut, lut_n);
