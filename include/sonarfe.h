@@ -256,6 +256,37 @@ SFE_API int sfe_frontend_run_host(sfe_frontend *fe, const uint8_t *frames_host, 
                                   int n_frames, int chunk_frames, float *T_host, int32_t *iters_host,
                                   int32_t *inliers_host, int32_t *status_host, int32_t *npoints_host);
 
+/* ------------------------------------------------------------------ global-initialisation cost (next row N2)
+ * SLAM.get_matching_cost_subroutine1 (slam.py:461-570), the function scipy.shgo minimises in
+ * initialize_sequential_scan_matching (slam.py:683-701) and initialize_nonsequential_scan_matching
+ * (slam.py:943-961): an occupancy grid of the target cloud at `resolution` (= point_noise / 10), dilated by an
+ * elliptical structuring element, and for a candidate transform the NEGATED number of transformed source points
+ * that land on an occupied cell.
+ *
+ * The grid geometry is computed by the caller exactly like slam.py:507-512 (xmin/ymin = cloud minimum minus
+ * 2 * point_noise as float32; rows/cols = lengths of the two np.arange calls).  Cell of a point (slam.py:516-517,
+ * 556-557), all in float32 like numpy:  r = int(rint((y - ymin) / resolution)), c = int(rint((x - xmin) / resolution)),
+ * target cells clipped into the grid, source cells outside the grid not counted.  The structuring element is
+ * passed as one column span [se_lo[j], se_hi[j]) per row j of the (2 * dilate_hs + 1)^2 kernel (empty row: lo >= hi)
+ * -- for cv2.getStructuringElement(MORPH_ELLIPSE, ...) the caller evaluates OpenCV's span formula (slam.py:523-527).
+ * A candidate transform is 6 floats {r00, r01, r10, r11, tx, ty} = sample_transform.matrix().astype(float32)
+ * (slam_objects.py:195); points move as x' = fma(y, r01, x * r00) + tx (what numpy's float32 dot does).  */
+typedef struct sfe_costmap sfe_costmap;
+SFE_API int sfe_costmap_create(sfe_ctx *ctx, const float *target_xy_host, int n_target, float xmin, float ymin,
+                               float resolution, int rows, int cols, int dilate_hs, const int32_t *se_lo,
+                               const int32_t *se_hi, sfe_costmap **out);
+SFE_API void sfe_costmap_destroy(sfe_costmap *cm);
+/* the dilated grid as the reference holds it: uint8 [rows][cols], 0 or 255 */
+SFE_API int sfe_costmap_grid_host(sfe_ctx *ctx, const sfe_costmap *cm, uint8_t *grid_host);
+/* source cloud of the closure (kept on the device between evaluations) */
+SFE_API int sfe_costmap_set_source_host(sfe_ctx *ctx, sfe_costmap *cm, const float *source_xy_host, int n_source);
+/* cost[k] = -(number of source points on occupied cells under transform k); K candidates in one launch */
+SFE_API int sfe_costmap_score_host(sfe_ctx *ctx, const sfe_costmap *cm, const float *transforms_host, int n_candidates,
+                                   int32_t *cost_host);
+/* device flavour: source cloud, transforms and costs in device memory, asynchronous on the context's stream */
+SFE_API int sfe_costmap_score_dev(sfe_ctx *ctx, const sfe_costmap *cm, const float *source_xy_dev, int n_source,
+                                  const float *transforms_dev, int n_candidates, int32_t *cost_dev);
+
 #ifdef __cplusplus
 }
 #endif

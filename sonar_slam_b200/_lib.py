@@ -49,6 +49,8 @@ def load():
         _type_more(lib)
         lib.sfe_maps_destroy.argtypes = [c_void_p]
         lib.sfe_maps_destroy.restype = None
+        lib.sfe_costmap_destroy.argtypes = [c_void_p]
+        lib.sfe_costmap_destroy.restype = None
         lib.sfe_icp_status_message.argtypes = [c_int]
         lib.sfe_icp_status_message.restype = ctypes.c_char_p
         lib.sfe_icp_params_default.argtypes = [c_void_p]
@@ -70,6 +72,12 @@ def _type_more(lib):
 
 
 _EXTRA_SIGNATURES = {
+    "sfe_costmap_create": [c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int, c_int, c_int, c_void_p,
+                           c_void_p, ctypes.POINTER(c_void_p)],
+    "sfe_costmap_grid_host": [c_void_p, c_void_p, c_void_p],
+    "sfe_costmap_set_source_host": [c_void_p, c_void_p, c_void_p, c_int],
+    "sfe_costmap_score_host": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "sfe_costmap_score_dev": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "sfe_maps_create": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_double,
                         ctypes.POINTER(c_void_p)],
     "sfe_cart_points_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
@@ -197,6 +205,81 @@ class Maps:
     def close(self):
         if getattr(self, "handle", None):
             self.lib.sfe_maps_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ellipse_spans(hs):
+    """Column spans [lo, hi) per row of cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2*hs+1, 2*hs+1), (hs, hs))
+    (OpenCV's formula: dx = cvRound(c * sqrt((r*r - dy*dy) / (r*r))), columns c-dx .. c+dx); checked against
+    cv2 itself in tests/test_oracle_globalinit.py."""
+    k = 2 * int(hs) + 1
+    r = c = k // 2
+    inv_r2 = 1.0 / (r * r) if r else 0.0
+    lo, hi = np.zeros(k, np.int32), np.zeros(k, np.int32)
+    for i in range(k):
+        dy = i - r
+        dx = int(np.rint(c * np.sqrt((r * r - dy * dy) * inv_r2)))
+        lo[i], hi[i] = max(c - dx, 0), min(c + dx + 1, k)
+    return lo, hi
+
+
+class CostMap:
+    """Dilated occupancy grid of a target cloud on the device + candidate-pose scoring (sfe_costmap);
+    the state behind the closure of SLAM.get_matching_cost_subroutine1 (slam.py:461-570)."""
+
+    def __init__(self, ctx, target_points, xmin, ymin, resolution, rows, cols, dilate_hs, se_lo=None, se_hi=None):
+        tgt = np.ascontiguousarray(target_points, np.float32)
+        if tgt.ndim != 2 or tgt.shape[1] != 2:
+            raise ValueError("target_points must be [N, 2]")
+        if se_lo is None:
+            se_lo, se_hi = ellipse_spans(dilate_hs)
+        se_lo = np.ascontiguousarray(se_lo, np.int32)
+        se_hi = np.ascontiguousarray(se_hi, np.int32)
+        if len(se_lo) != 2 * dilate_hs + 1 or len(se_hi) != len(se_lo):
+            raise ValueError("structuring element needs 2*dilate_hs+1 row spans")
+        self.ctx, self.lib = ctx, ctx.lib
+        self.rows, self.cols = int(rows), int(cols)
+        h = c_void_p()
+        check(ctx.lib.sfe_costmap_create(ctx.handle, ptr(tgt), len(tgt), float(xmin), float(ymin), float(resolution),
+                                         self.rows, self.cols, int(dilate_hs), ptr(se_lo), ptr(se_hi),
+                                         ctypes.byref(h)), "sfe_costmap_create")
+        self.handle = h
+
+    def grid(self):
+        out = np.empty((self.rows, self.cols), np.uint8)
+        check(self.lib.sfe_costmap_grid_host(self.ctx.handle, self.handle, ptr(out)), "sfe_costmap_grid_host")
+        return out
+
+    def set_source(self, source_points):
+        src = np.ascontiguousarray(source_points, np.float32)
+        if src.ndim != 2 or src.shape[1] != 2:
+            raise ValueError("source_points must be [N, 2]")
+        check(self.lib.sfe_costmap_set_source_host(self.ctx.handle, self.handle, ptr(src), len(src)),
+              "sfe_costmap_set_source_host")
+
+    def score(self, transforms):
+        """transforms: [K, 6] float32 rows (r00, r01, r10, r11, tx, ty) -> int32 [K] costs."""
+        tf = np.ascontiguousarray(transforms, np.float32).reshape(-1, 6)
+        cost = np.empty(len(tf), np.int32)
+        check(self.lib.sfe_costmap_score_host(self.ctx.handle, self.handle, ptr(tf), len(tf), ptr(cost)),
+              "sfe_costmap_score_host")
+        return cost
+
+    def score_dev(self, source_dev_ptr, n_source, transforms_dev_ptr, n_candidates, cost_dev_ptr, ctx=None):
+        """Asynchronous on the stream of `ctx` (default: the context the map was built with)."""
+        check(self.lib.sfe_costmap_score_dev((ctx or self.ctx).handle, self.handle, c_void_p(source_dev_ptr), int(n_source),
+                                             c_void_p(transforms_dev_ptr), int(n_candidates), c_void_p(cost_dev_ptr)),
+              "sfe_costmap_score_dev")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.sfe_costmap_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -1,6 +1,7 @@
 """Scan-matching helpers of the reference's `SLAM` class, ROS- and gtsam-free
 (bruce_slam/src/bruce_slam/slam.py: compute_icp :294-323, compute_icp_with_cov :325-387,
-get_overlap :389-424, get_points :229-292; Keyframe.transform_points slam_objects.py:178-198).
+get_overlap :389-424, get_points :229-292, get_matching_cost_subroutine1 :461-570 and the shgo call around
+it :683-701 / :943-961; Keyframe.transform_points slam_objects.py:178-198).
 
 The pose-graph part of SLAM (ISAM2, PCM, keyframe logic) is out of this library's scope and stays
 with the caller; `Pose2` below is a minimal stand-in for gtsam.Pose2 (x, y, theta, matrix,
@@ -11,6 +12,7 @@ import time as time_pkg
 import numpy as np
 
 from . import pcl
+from .. import _lib
 
 try:  # pragma: no cover - gtsam is not installed in the build image
     from gtsam import Pose2
@@ -118,6 +120,86 @@ class SLAM(object):
         if return_indices:
             return np.sum(indices != -1), indices
         return np.sum(indices != -1)
+
+    # ---- slam.py:461-570
+    def get_matching_cost_subroutine1(self, source_points, source_pose, target_points, target_pose,
+                                      source_pose_cov=None):
+        """Returns (subroutine, pose_samples) like the reference: `subroutine(x)` is the cost scipy.shgo minimises
+        (minus the number of source points that fall on the dilated target grid under the pose x = [x, y, theta]
+        composed onto source_pose) and every evaluation appends [pose, cost] to pose_samples.  Grid and source
+        cloud live on the GPU; `subroutine.batch(xs)` scores K poses in one launch."""
+        pose_samples = []
+        source_points = np.ascontiguousarray(source_points, np.float32)
+        target_points = np.ascontiguousarray(target_points, np.float32)
+
+        # grid geometry: the reference's own expressions (slam.py:507-512, 522-523), evaluated by numpy
+        xmin, ymin = np.min(target_points, axis=0) - 2 * self.point_noise
+        xmax, ymax = np.max(target_points, axis=0) + 2 * self.point_noise
+        resolution = self.point_noise / 10.0
+        xs = np.arange(xmin, xmax, resolution)
+        ys = np.arange(ymin, ymax, resolution)
+        dilate_hs = int(np.ceil(self.point_noise / resolution))
+        source_pose_info = np.linalg.inv(source_pose_cov)  # noqa: F841 (computed and unused upstream, slam.py:539)
+
+        costmap = _lib.CostMap(_lib.default_context(), target_points, xmin, ymin, resolution, len(ys), len(xs),
+                               dilate_hs)
+        costmap.set_source(source_points)
+
+        def sample_poses(x):
+            delta = Pose2(*x)
+            sample_source_pose = source_pose.compose(delta)
+            sample_transform = target_pose.between(sample_source_pose)
+            return sample_source_pose, sample_transform
+
+        def as_row(transform):
+            T = transform.matrix().astype(np.float32)  # Keyframe.transform_points, slam_objects.py:195
+            return [T[0, 0], T[0, 1], T[1, 0], T[1, 1], T[0, 2], T[1, 2]]
+
+        def subroutine(x):
+            sample_source_pose, sample_transform = sample_poses(x)
+            cost = int(costmap.score(np.array([as_row(sample_transform)], np.float32))[0])
+            pose_samples.append(np.r_[sample_source_pose.x(), sample_source_pose.y(), sample_source_pose.theta(), cost])
+            return cost
+
+        def batch(xs, log=True):
+            """Costs of K poses [K, 3] in one launch (what a dense sampler uses instead of K shgo evaluations)."""
+            xs = np.atleast_2d(np.asarray(xs, np.float64))
+            poses = [sample_poses(x) for x in xs]
+            costs = costmap.score(np.array([as_row(t) for _, t in poses], np.float32))
+            if log:
+                for (sp, _), c in zip(poses, costs):
+                    pose_samples.append(np.r_[sp.x(), sp.y(), sp.theta(), int(c)])
+            return costs
+
+        subroutine.batch = batch
+        subroutine.costmap = costmap
+        return subroutine, pose_samples
+
+    # ---- slam.py:667-701 (SSM) / :927-961 (NSSM): the shgo call, or one dense Sobol batch on the GPU
+    def global_initialization(self, source_points, source_pose, target_points, target_pose, cov, pose_bounds,
+                              initialization_params=(50, 1, 0.01), dense=0):
+        """dense = 0: scipy.shgo exactly as the reference calls it (sobol sampling, n, iters, ftol), evaluating the
+        GPU subroutine point by point.  dense = K > 0: score K Sobol poses inside pose_bounds in ONE launch and take
+        the best (the cost is piecewise constant, so shgo's local SLSQP stage cannot improve on a sample)."""
+        subroutine, pose_samples = self.get_matching_cost_subroutine1(source_points, source_pose, target_points,
+                                                                      target_pose, cov)
+        pose_bounds = np.asarray(pose_bounds, np.float64)
+        if dense:
+            from scipy.stats import qmc
+            unit = qmc.Sobol(d=3, scramble=False).random(int(dense))
+            xs = pose_bounds[:, 0] + unit * (pose_bounds[:, 1] - pose_bounds[:, 0])
+            costs = subroutine.batch(xs)
+            best = int(np.argmin(costs))  # first minimum, like a sequential scan of the samples
+            return dict(success=True, x=xs[best], fun=float(costs[best]), pose_samples=np.array(pose_samples),
+                        estimated_source_pose=source_pose.compose(Pose2(*xs[best])))
+        from scipy.optimize import shgo
+        result = shgo(func=subroutine, bounds=pose_bounds, n=initialization_params[0], iters=initialization_params[1],
+                      sampling_method="sobol", minimizer_kwargs={"options": {"ftol": initialization_params[2]}})
+        out = dict(success=bool(result.success), x=result.x, fun=float(result.fun), message=result.message,
+                   pose_samples=np.array(pose_samples))
+        if result.success:
+            out["estimated_source_pose"] = source_pose.compose(Pose2(*result.x))
+        return out
 
     # ---- slam.py:229-292 for (points, pose) keyframe tuples
     def get_points(self, frames=None, ref_frame=None, return_keys=False):

@@ -42,7 +42,8 @@ namespace sfe {
 
 constexpr int CF_W = 128;     // beams per strip / consumer threads per CTA
 constexpr int CF_CH = 16;     // range bins per TMA box
-constexpr int CF_NSTAGE = 4;  // input ring depth (stages of CF_CH rows)
+constexpr int CF_NSTAGE = 4;     // input ring depth (stages of CF_CH rows); 2 is 20 % slower, 8 no faster (B200)
+constexpr int CF_NSTAGE_U8 = 4;  // same for the uint8 kernel
 constexpr int CF_RING = 32;   // two 32-deep register rings per thread (cells, window sums)
 constexpr int CF_T = 20;      // train_hs of the streaming path
 constexpr int CF_G = 5;       // guard_hs of the streaming path
@@ -141,14 +142,14 @@ __device__ __noinline__ void cfar_resolve_block(const CfarParams &p, uint8_t (*o
 
 // Input ring without a producer warp.  Every 16-row block reads its two TMA boxes into registers up
 // front and ends with a CTA-wide barrier, so after the barrier of block `blk` box blk-1 is dead and its
-// stage can take box blk + CF_NSTAGE - 1: one thread re-arms the stage's mbarrier and issues the load.
-template <typename InT>
+// stage can take box blk + NS - 1 (NS = ring depth): one thread re-arms the stage's mbarrier and issues the load.
+template <typename InT, int NS>
 __device__ __forceinline__ void cfar_refill(InT (*tile)[CF_CH][CF_W], uint64_t *full_bar, const CUtensorMap *in_map,
                                             const int blk, const int nchunks, const int tid, const int f,
                                             const int col0) {
-  const int c = blk + CF_NSTAGE - 1;
+  const int c = blk + NS - 1;
   if (tid == 0 && c < nchunks) {
-    const int st = c & (CF_NSTAGE - 1);
+    const int st = c & (NS - 1);
     mbar_arrive_expect_tx(&full_bar[st], CF_CH * CF_W * (int)sizeof(InT));
     tma_load_3d(&tile[st][0][0], in_map, &full_bar[st], col0, c * CF_CH, f);
   }
@@ -247,7 +248,7 @@ __device__ __forceinline__ void cfar_block16(CfarStep &s, InT (*tile)[CF_CH][CF_
 #undef SFE_STEP
   if (EDGE && r0 < 0) {  // priming blocks: no output rows
     named_bar_sync(1, CF_W);
-    cfar_refill<InT>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
+    cfar_refill<InT, CF_NSTAGE>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
     return;
   }
   if (!WITH_THR && amb) {
@@ -267,7 +268,7 @@ __device__ __forceinline__ void cfar_block16(CfarStep &s, InT (*tile)[CF_CH][CF_
   if (MASK) fence_proxy_async_smem();
   if (MASK && tid == 0) tma_wait_read<0>();  // the other buffer's TMA store has finished reading it
   named_bar_sync(1, CF_W);
-  cfar_refill<InT>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
+  cfar_refill<InT, CF_NSTAGE>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
   if (MASK && tid == 0) {
     tma_store_3d(p.out_map, &obuf[ob][0][0], col0, r0, f);
     tma_commit();
@@ -389,15 +390,15 @@ __device__ __forceinline__ void cfar_block16_u8(CfarStepI &s, uint8_t (*tile)[CF
   const int cA = blk - 1, cB = blk;
   const bool hasA = EDGE ? (cA >= 0 && cA < nchunks) : true;
   const bool hasB = EDGE ? (cB < nchunks) : true;
-  const uint8_t(*tileA)[CF_W] = tile[cA & (CF_NSTAGE - 1)];
-  const uint8_t(*tileB)[CF_W] = tile[cB & (CF_NSTAGE - 1)];
+  const uint8_t(*tileA)[CF_W] = tile[cA & (CF_NSTAGE_U8 - 1)];
+  const uint8_t(*tileB)[CF_W] = tile[cB & (CF_NSTAGE_U8 - 1)];
   constexpr int ob = Q & 1;
   const bool col_ok = col0 + tid < p.B;
   unsigned keep_bits = 0;
   int xin[CF_CH];
 #pragma unroll
   for (int i = 0; i < CF_SPLIT; ++i) xin[i] = (!EDGE || hasA) ? (int)tileA[i + CF_CH - CF_SPLIT][tid] : 0;
-  if (hasB) mbar_wait(&full_bar[cB & (CF_NSTAGE - 1)], (cB / CF_NSTAGE) & 1);
+  if (hasB) mbar_wait(&full_bar[cB & (CF_NSTAGE_U8 - 1)], (cB / CF_NSTAGE_U8) & 1);
 #pragma unroll
   for (int i = CF_SPLIT; i < CF_CH; ++i) xin[i] = (!EDGE || hasB) ? (int)tileB[i - CF_SPLIT][tid] : 0;
 #define SFE_STEP(I) \
@@ -407,14 +408,14 @@ __device__ __forceinline__ void cfar_block16_u8(CfarStepI &s, uint8_t (*tile)[CF
 #undef SFE_STEP
   if (EDGE && r0 < 0) {
     named_bar_sync(1, CF_W);
-    cfar_refill<uint8_t>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
+    cfar_refill<uint8_t, CF_NSTAGE_U8>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
     return;
   }
   if (BITS && (tid & 31) < CF_CH) obits[ob][tid & 31][tid >> 5] = keep_bits;
   if (MASK) fence_proxy_async_smem();
   if (MASK && tid == 0) tma_wait_read<0>();
   named_bar_sync(1, CF_W);
-  cfar_refill<uint8_t>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
+  cfar_refill<uint8_t, CF_NSTAGE_U8>(tile, full_bar, in_map, blk, nchunks, tid, f, col0);
   if (MASK && tid == 0) {
     tma_store_3d(p.out_map, &obuf[ob][0][0], col0, r0, f);
     tma_commit();
@@ -431,10 +432,10 @@ template <int ALG, bool MASK, bool BITS>
 __global__ void __launch_bounds__(CF_W, 5)
     cfar_u8_lut_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                        CfarParams p, const uint16_t *__restrict__ lut_g, const int lut_n) {
-  __shared__ __align__(128) uint8_t tile[CF_NSTAGE][CF_CH][CF_W];
+  __shared__ __align__(128) uint8_t tile[CF_NSTAGE_U8][CF_CH][CF_W];
   __shared__ __align__(128) uint8_t obuf[2][CF_CH][CF_W];
   __shared__ uint32_t obits[2][CF_CH][CF_W / 32];
-  __shared__ __align__(8) uint64_t full_bar[CF_NSTAGE];
+  __shared__ __align__(8) uint64_t full_bar[CF_NSTAGE_U8];
   __shared__ __align__(16) uint16_t lut[(ALG == SFE_CFAR_CA ? CF_LUT_MAX : CF_T * 255 + 1) + 7];
 
   const int tid = threadIdx.x;
@@ -446,9 +447,9 @@ __global__ void __launch_bounds__(CF_W, 5)
 
   if (tid == 0) {
     prefetch_tmap(&in_map);
-    for (int st = 0; st < CF_NSTAGE; ++st) mbar_init(&full_bar[st], 1);
+    for (int st = 0; st < CF_NSTAGE_U8; ++st) mbar_init(&full_bar[st], 1);
     fence_mbar_init();
-    for (int c = 0; c < CF_NSTAGE - 1 && c < nchunks; ++c) {
+    for (int c = 0; c < CF_NSTAGE_U8 - 1 && c < nchunks; ++c) {
       mbar_arrive_expect_tx(&full_bar[c], CF_CH * CF_W);
       tma_load_3d(&tile[c][0][0], &in_map, &full_bar[c], col0, c * CF_CH, f);
     }

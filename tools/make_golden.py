@@ -22,6 +22,11 @@ Fixtures written:
   tests/golden/featx_config1.npz    FeatureExtraction.callback on the config-1 ping:
                                     map_x/map_y digests + samples, Cartesian (row,col)
                                     list and the metric points it publishes
+  tests/golden/globalinit.npz       SLAM.get_matching_cost_subroutine1 (slam.py:461-570) run
+                                    unmodified on a synthetic source/target pair: the dilated
+                                    target grid (packed) and the cost of 96 candidate poses.
+                                    gtsam is absent: gtsam.Pose2 is replaced by the SE(2) class
+                                    of oracle/globalinit_ref.py, everything else is the reference
 """
 import hashlib
 import importlib
@@ -70,9 +75,24 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         pass
 
 
+def _install_gtsam_stub():
+    """gtsam with a working Pose2 (the cost function composes poses); the rest stays a mock."""
+    from oracle import globalinit_ref
+
+    g = _StubModule("gtsam")
+    g.__path__ = []
+    g.Pose2 = globalinit_ref.Pose2
+    for name in ("Rot3", "Pose3"):  # conversions.g2n does isinstance() against these
+        setattr(g, name, type(name, (), {}))
+    g.Point2 = lambda *a: np.zeros(2)
+    g.Point3 = lambda *a: np.zeros(3)
+    sys.modules["gtsam"] = g
+
+
 def _install_reference():
     from oracle import oracle as orc
 
+    _install_gtsam_stub()
     sys.meta_path.insert(0, _StubFinder())
     sys.path.insert(0, REF_SRC)
     pkg = importlib.import_module("bruce_slam")
@@ -182,6 +202,29 @@ def main():
         assert len(locs) == len(pts)
         print(tag, "rows/cols", fe.rows, fe.cols, "polar det", int(peaks.sum()), "cart px", len(locs))
     np.savez_compressed(os.path.join(out, "featx_config1.npz"), **res)
+
+    # ---- SLAM.get_matching_cost_subroutine1 on a synthetic pair -------------------
+    slam_mod = importlib.import_module("bruce_slam.slam")
+    gtsam = sys.modules["gtsam"]
+    src, tgt, _ = synth.make_icp_pair(7, n_source=700, n_target=5000, extent=36.0, sensor_range=18.0)
+    source_pose, target_pose = gtsam.Pose2(3.0, -1.5, 0.4), gtsam.Pose2(2.6, -1.1, 0.33)
+    # the function is used unbound: it only reads self.point_noise (slam.py:73)
+    fake_self = types.SimpleNamespace(point_noise=0.5)
+    subroutine, pose_samples = slam_mod.SLAM.get_matching_cost_subroutine1(
+        fake_self, src, source_pose, tgt, target_pose, np.diag([0.04, 0.04, 0.0004]))
+    cells = {c.cell_contents.shape: c.cell_contents for c in subroutine.__closure__
+             if isinstance(c.cell_contents, np.ndarray) and c.cell_contents.ndim == 2
+             and c.cell_contents.dtype == np.uint8}
+    (grid,) = cells.values()
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([np.zeros((1, 3)), rng.uniform(-1, 1, (95, 3)) * np.array([1.0, 1.0, 0.1])])
+    xs[1] = [0.4, -0.4, 0.07]
+    costs = np.array([subroutine(x) for x in xs], np.int64)
+    gi = dict(source=src, target=tgt, source_pose=np.array([3.0, -1.5, 0.4]), target_pose=np.array([2.6, -1.1, 0.33]),
+              xs=xs, costs=costs, pose_samples=np.array(pose_samples), grid_shape=np.array(grid.shape, np.int64),
+              grid_packed=np.packbits(grid > 0), grid_sha256=np.array(_digest(grid)))
+    np.savez_compressed(os.path.join(out, "globalinit.npz"), **gi)
+    print("globalinit: grid", grid.shape, "occupied", int((grid > 0).sum()), "costs", costs[:6], "min", costs.min())
     print("golden fixtures written to", out)
 
 
