@@ -147,15 +147,31 @@ struct NNResult {
 };
 
 // scan a contiguous range of sorted points (hot loop: no global memory, ties only flagged)
+__device__ __forceinline__ void nn_update(float d2, int p, NNResult &r) {
+  r.tie |= (d2 == r.d2) & (p != r.pos);
+  if (d2 < r.d2) {
+    r.d2 = d2;
+    r.pos = p;
+    r.tie = 0;
+  }
+}
+
+// Four candidates per trip: the four shared-memory loads are issued together (a warp issues in order, so a
+// load followed by its use costs the full latency per candidate), and the best / tie bookkeeping only runs
+// when one of the four is at least as close as the current best -- O(log n) times per query.  Positions past
+// the end are clamped to e - 1: re-evaluating a candidate never changes the result (same position, no tie).
 __device__ __forceinline__ void nn_scan(const GridView &g, int s, int e, float qx, float qy, NNResult &r) {
-  for (int p = s; p < e; ++p) {
-    const float2 t = g.pts[p];
-    const float d2 = dist2_rn(qx - t.x, qy - t.y);
-    r.tie |= (d2 == r.d2) & (p != r.pos);
-    if (d2 < r.d2) {
-      r.d2 = d2;
-      r.pos = p;
-      r.tie = 0;
+  const int last = e - 1;
+  for (int p = s; p < e; p += 4) {
+    const int p1 = min(p + 1, last), p2 = min(p + 2, last), p3 = min(p + 3, last);
+    const float2 t0 = g.pts[p], t1 = g.pts[p1], t2 = g.pts[p2], t3 = g.pts[p3];
+    const float d0 = dist2_rn(qx - t0.x, qy - t0.y), d1 = dist2_rn(qx - t1.x, qy - t1.y);
+    const float d2 = dist2_rn(qx - t2.x, qy - t2.y), d3 = dist2_rn(qx - t3.x, qy - t3.y);
+    if (fminf(fminf(d0, d1), fminf(d2, d3)) <= r.d2) {
+      nn_update(d0, p, r);
+      nn_update(d1, p1, r);
+      nn_update(d2, p2, r);
+      nn_update(d3, p3, r);
     }
   }
 }
