@@ -176,18 +176,23 @@ __device__ __forceinline__ void nn_scan(const GridView &g, int s, int e, float q
   }
 }
 
-// rare: among the points of the (2k+1)^2 block at exactly distance r.d2, keep the lowest original index
-static __device__ __noinline__ void nn_resolve_tie(const GridView &g, int cx, int cy, int k, float qx, float qy, NNResult &r) {
+// rare: among the points of the cell rectangle [xa, xb] x [ya, yb] at exactly distance r.d2, keep the lowest
+// original index
+static __device__ __noinline__ void nn_resolve_tie_rect(const GridView &g, int xa, int xb, int ya, int yb, float qx,
+                                                        float qy, NNResult &r) {
   if (g.orig == nullptr || r.pos < 0) return;
-  const int xa = max(cx - k, 0), xb = min(cx + k, g.nx - 1);
   int best = r.pos;
-  for (int y = max(cy - k, 0); y <= min(cy + k, g.ny - 1); ++y)
+  for (int y = ya; y <= yb; ++y)
     for (int p = g.cstart[y * g.nx + xa]; p < g.cstart[y * g.nx + xb + 1]; ++p) {
       const float2 t = g.pts[p];
       if (dist2_rn(qx - t.x, qy - t.y) == r.d2 && g.orig[p] < g.orig[best]) best = p;
     }
   r.pos = best;
   r.tie = 0;
+}
+
+__device__ __forceinline__ void nn_resolve_tie(const GridView &g, int cx, int cy, int k, float qx, float qy, NNResult &r) {
+  nn_resolve_tie_rect(g, max(cx - k, 0), min(cx + k, g.nx - 1), max(cy - k, 0), min(cy + k, g.ny - 1), qx, qy, r);
 }
 
 // conservative lower bound (squared) on the distance from the query to anything outside the
@@ -267,6 +272,24 @@ __device__ __forceinline__ NNResult nn_query(const GridView &g, float qx, float 
     r.d2 = INFINITY;
   }
   return r;
+}
+
+// Exact nearest neighbour when a good candidate is already known (ICP: the match of the previous iteration).
+// The candidate's distance d bounds the answer, so only the cells that overlap the disc of radius d around the
+// query can hold the nearest neighbour or a tie with it -- typically 1-4 cells instead of the 3x3 block and its
+// successors.  The result (position, distance, tie rule) is the same as nn_query's.
+__device__ __forceinline__ NNResult nn_query_seeded(const GridView &g, float qx, float qy, float max_d2, int seed) {
+  const float2 t = g.pts[seed];
+  const float d0 = dist2_rn(qx - t.x, qy - t.y);
+  if (!(d0 <= max_d2)) return nn_query(g, qx, qy, max_d2);  // the seed itself is not acceptable any more (or NaN)
+  const float rad = sqrtf(d0) * 1.0001f + 1e-4f * g.cell;   // conservative against the rounding of d0 and of q -+ rad
+  const int xa = grid_cell_coord(qx - rad, g.ox, g.inv_cell, g.nx), xb = grid_cell_coord(qx + rad, g.ox, g.inv_cell, g.nx);
+  const int ya = grid_cell_coord(qy - rad, g.oy, g.inv_cell, g.ny), yb = grid_cell_coord(qy + rad, g.oy, g.inv_cell, g.ny);
+  NNResult r;
+  r.d2 = INFINITY, r.pos = -1, r.tie = 0;
+  for (int y = ya; y <= yb; ++y) nn_scan(g, g.cstart[y * g.nx + xa], g.cstart[y * g.nx + xb + 1], qx, qy, r);
+  if (r.tie) nn_resolve_tie_rect(g, xa, xb, ya, yb, qx, qy, r);
+  return r;  // r.pos >= 0: the seed's own cell is inside the rectangle
 }
 
 }  // namespace sfe

@@ -178,6 +178,7 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
 __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [IcpShared][sorted float2 nt_max][cells u32][reading float2 ns_max][dist f32 ns_max][match u16 ns_max]
+  //         [prev u16 ns_max][qstate u8 ns_max]
   IcpShared &sh = *reinterpret_cast<IcpShared *>(smem_raw);
   size_t off = (sizeof(IcpShared) + 15) & ~size_t(15);
   float2 *sorted = reinterpret_cast<float2 *>(smem_raw + off);
@@ -190,6 +191,8 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
   float *dist = reinterpret_cast<float *>(smem_raw + off);
   off += sizeof(float) * (size_t)b.ns_max;
   uint16_t *match = reinterpret_cast<uint16_t *>(smem_raw + off);
+  off += sizeof(uint16_t) * (size_t)b.ns_max;
+  uint16_t *prev = reinterpret_cast<uint16_t *>(smem_raw + off);  // NN of the previous iteration (search seed)
   off += sizeof(uint16_t) * (size_t)b.ns_max;
   uint8_t *qstate = reinterpret_cast<uint8_t *>(smem_raw + off);
 
@@ -302,7 +305,10 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
       sh.iterate = 1;
     }
     __syncthreads();
-    for (int i = tid; i < ns; i += nthr) reading[i] = apply_T(sh.T0, src[2 * i], src[2 * i + 1]);
+    for (int i = tid; i < ns; i += nthr) {
+      reading[i] = apply_T(sh.T0, src[2 * i], src[2 * i + 1]);
+      prev[i] = 0xffff;
+    }
     __syncthreads();
 
     // ---- 3. iterations
@@ -326,9 +332,10 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
       if (small) {
         for (int i = tid; i < ns; i += nthr) {
           const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-          const NNResult r = nn_query(g, q.x, q.y, max_d2);
+          const int seed = prev[i];
+          const NNResult r = seed != 0xffff ? nn_query_seeded(g, q.x, q.y, max_d2, seed) : nn_query(g, q.x, q.y, max_d2);
           dist[i] = r.d2;
-          match[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
+          match[i] = prev[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
           n_fin += r.pos >= 0;
         }
       }
@@ -337,7 +344,16 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
         NNResult r;
         r.d2 = INFINITY, r.pos = -1, r.tie = 0;
-        const int exact = nn_search(g, q.x, q.y, max_d2, stop_a, -1, r);  // own cell, then at most the 3x3 block
+        int exact;
+        const int seed = prev[i];
+        const float2 ts = sorted[seed != 0xffff ? seed : 0];
+        if (seed != 0xffff && dist2_rn(q.x - ts.x, q.y - ts.y) <= stop_a) {
+          r = nn_query_seeded(g, q.x, q.y, max_d2, seed);  // last iteration's match is still close: settle it now
+          exact = 1;
+        } else {
+          exact = nn_search(g, q.x, q.y, max_d2, stop_a, -1, r);  // own cell, then at most the 3x3 block
+        }
+        if (exact) prev[i] = (r.pos >= 0 && r.d2 <= max_d2) ? (uint16_t)r.pos : (uint16_t)0xffff;
         const bool fin = r.pos >= 0 && r.d2 <= max_d2;
         dist[i] = fin ? r.d2 : INFINITY;
         match[i] = fin ? (uint16_t)r.pos : (uint16_t)0xffff;
@@ -419,7 +435,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
           if (exact) {
             const bool fin = r.pos >= 0 && r.d2 <= max_d2;  // == the finiteness found in pass B
             dist[i] = fin ? r.d2 : INFINITY;
-            match[i] = fin ? (uint16_t)r.pos : (uint16_t)0xffff;
+            match[i] = prev[i] = fin ? (uint16_t)r.pos : (uint16_t)0xffff;
           } else {
             dist[i] = ICP_PRUNED;  // finite, farther than the quantile bound: weight 0
             match[i] = 0xffff;
@@ -673,7 +689,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   b.prm = *prm;
   size_t smem = ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
                 sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
-                sizeof(float) * (size_t)b.ns_max + sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 16;
+                sizeof(float) * (size_t)b.ns_max + 2 * sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 16;
   if (smem > (size_t)ctx->max_smem_optin) {
     set_error("icp: source %d + target %d points need %zu B of shared memory per CTA (limit %d)", ns_max, nt_max, smem,
               ctx->max_smem_optin);
