@@ -168,7 +168,7 @@ typedef struct {
   int max_iterations;     /* CounterTransformationChecker               icp.yaml:24    40 */
   float min_diff_rot;     /* DifferentialTransformationChecker          icp.yaml:26  0.01 */
   float min_diff_trans;   /*                                            icp.yaml:27   0.1 */
-  int smooth_length;      /* (0: differential checker off)              icp.yaml:28     4 */
+  int smooth_length;      /* (0: differential checker off; <= 15)        icp.yaml:28     4 */
   int flags;              /* bit 0: MaxDist filter compares squared distance with maxDist itself */
 } sfe_icp_params;
 SFE_API void sfe_icp_params_default(sfe_icp_params *p);

@@ -21,7 +21,7 @@
 namespace sfe {
 
 constexpr int ICP_THREADS = 512;
-constexpr int ICP_HIST = 64;  // differential-checker history kept (>= smoothLength + 1)
+constexpr int ICP_HIST = 16;  // differential-checker history kept (>= smoothLength + 1)
 constexpr int ICP_COARSE = 8;            // fine cells per coarse cell edge
 constexpr int ICP_COARSE_WORDS = 96;     // bitmap words: cnx*cny <= 2048 + margin
 constexpr float ICP_PRUNED = 3.0e38f;    // "finite, but farther than we needed to know"
@@ -89,31 +89,43 @@ __device__ __forceinline__ void rot_to_quat(const float *T, float &qw, float &qz
   }
 }
 
-// sum K doubles over the CTA; result valid in out[0..K) for every thread after the call
+// Sum K doubles over the CTA with ONE barrier: every warp publishes its partial sums, and after the barrier
+// every warp reduces the (<= 16) partials itself with a butterfly, so all threads hold the bit-identical total.
+// `scratch` has two halves used alternately (`phase` counts the calls): the half written by call n is last read
+// before call n+1's barrier and not rewritten before call n+2.
 template <int K>
-__device__ __forceinline__ void block_sum(double (&v)[K], double *scratch /* [K][32] smem */, double (&out)[K]) {
+__device__ __forceinline__ void block_sum(double (&v)[K], double *scratch /* [2][5][16] smem */, int &phase,
+                                          double (&out)[K]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  static_assert(K <= 5, "scratch holds five partial sums per warp");
+  double *half = scratch + (phase & 1) * (5 * 16);
+  ++phase;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double x = v[k];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
-    if (lane == 0) scratch[k * 32 + warp] = x;
-  }
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      double x = lane < nwarps ? scratch[k * 32 + lane] : 0.0;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
-      if (lane == 0) scratch[k * 32] = x;
-    }
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (lane == 0) half[k * 16 + warp] = x;
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < K; ++k) out[k] = scratch[k * 32];
+  for (int k = 0; k < K; ++k) {
+    double x = lane < nwarps ? half[k * 16 + lane] : 0.0;
+#pragma unroll
+    for (int d = 8; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);  // nwarps <= 16
+    out[k] = __shfl_sync(0xffffffffu, x, 0);
+  }
+}
+
+// same for one int
+__device__ __forceinline__ int block_total(int v, int *scratch /* [2][16] smem */, int &phase) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  int *half = scratch + (phase & 1) * 16;
+  ++phase;
+  v = __reduce_add_sync(0xffffffffu, v);
+  if (lane == 0) half[warp] = v;
   __syncthreads();
+  return __reduce_add_sync(0xffffffffu, lane < nwarps ? half[lane] : 0);
 }
 
 struct IcpShared {  // small fixed-size part of the shared state
@@ -123,9 +135,11 @@ struct IcpShared {  // small fixed-size part of the shared state
   float bbox[4];
   int iterate, status, count, inliers;
   int sel_bin, sel_k;
-  int hist[256];
+  int hist[3][256];  // radix-select histograms, used in rotation (block_select_kth)
   int scan[36];
-  double red[8 * 32];
+  int tot[2][16];
+  double red[2 * 5 * 16];  // <= 16 warps per CTA
+  float wred[4 * 16];      // per-warp partials of the bounding-box / maximum reductions
   float hq_w[ICP_HIST], hq_z[ICP_HIST], ht_x[ICP_HIST], ht_y[ICP_HIST];
   int hn;
   int cnx, cny;               // coarse occupancy grid (ICP_COARSE x ICP_COARSE fine cells per coarse cell)
@@ -134,44 +148,48 @@ struct IcpShared {  // small fixed-size part of the shared state
 
 // k-th smallest (0-based) of the finite entries of vals[0..n): 4-pass radix select on the float bits
 // (non-negative floats order like their bit patterns).  All threads call it; kk < number of finite entries.
-__device__ __forceinline__ float block_select_kth(const float *vals, int n, int kk, IcpShared &sh) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+// One barrier per pass: pass number `pass` (counted over the CTA's lifetime) fills histogram pass % 3 and clears
+// histogram (pass + 1) % 3 -- last read two passes ago -- before its barrier; after the barrier every warp scans
+// the 256 bins itself (8 per lane), so no second barrier is needed to publish the selected bin.
+__device__ __forceinline__ float block_select_kth(const float *vals, int n, int kk, IcpShared &sh, int &pass) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
   uint32_t prefix = 0, mask = 0;
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int h = tid; h < 256; h += nthr) sh.hist[h] = 0;
-    __syncthreads();
+    int *hist = sh.hist[pass % 3], *next = sh.hist[(pass + 1) % 3];
+    ++pass;
+    for (int h = tid; h < 256; h += nthr) next[h] = 0;
     for (int i = tid; i < n; i += nthr) {
       const float v = vals[i];
       if (!(v < INFINITY)) continue;
       const uint32_t u = __float_as_uint(v);
-      if ((u & mask) == prefix) atomicAdd(&sh.hist[(u >> shift) & 255u], 1);
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1);
     }
     __syncthreads();
-    if (tid < 32) {  // lane l owns bins 8l .. 8l+7
-      int c[8], sum = 0;
+    int c[8], sum = 0;  // lane l owns bins 8l .. 8l+7
 #pragma unroll
-      for (int j = 0; j < 8; ++j) c[j] = sh.hist[tid * 8 + j], sum += c[j];
-      int incl = sum;
+    for (int j = 0; j < 8; ++j) c[j] = hist[lane * 8 + j], sum += c[j];
+    int incl = sum;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (tid >= d) incl += t;
-      }
-      int run = incl - sum;
-      if (kk >= run && kk < incl) {
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    int run = incl - sum, bin = 255, kn = 0;
+    const bool mine = kk >= run && kk < incl;
+    if (mine) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (kk >= run && kk < run + c[j]) sh.sel_bin = tid * 8 + j, sh.sel_k = kk - run;
-          run += c[j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        if (kk >= run && kk < run + c[j]) bin = lane * 8 + j, kn = kk - run;
+        run += c[j];
       }
     }
-    __syncthreads();
-    prefix |= (uint32_t)sh.sel_bin << shift;
+    const unsigned owner = __ballot_sync(0xffffffffu, mine);
+    const int src = owner ? __ffs(owner) - 1 : 31;
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    kk = __shfl_sync(0xffffffffu, kn, src);
+    prefix |= (uint32_t)bin << shift;
     mask |= 255u << shift;
-    kk = sh.sel_k;
   }
-  __syncthreads();
   return __uint_as_float(prefix);
 }
 
@@ -197,6 +215,8 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
   uint8_t *qstate = reinterpret_cast<uint8_t *>(smem_raw + off);
 
   const int tid = threadIdx.x, nthr = blockDim.x;
+  int red_phase = 0, tot_phase = 0, sel_pass = 0;  // rotation counters of the one-barrier reductions (CTA-uniform)
+  for (int h = threadIdx.x; h < 3 * 256; h += blockDim.x) (&sh.hist[0][0])[h] = 0;
   uint16_t *orig = b.orig_ws + (size_t)blockIdx.x * b.nt_max;
   const sfe_icp_params prm = b.prm;
   const float max_d2 = __fmul_rn(prm.matcher_max_dist, prm.matcher_max_dist);
@@ -234,7 +254,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
     {
       double s[2] = {0.0, 0.0}, tot[2];
       for (int i = tid; i < nt; i += nthr) s[0] += (double)tgt[2 * i], s[1] += (double)tgt[2 * i + 1];
-      block_sum<2>(s, sh.red, tot);
+      block_sum<2>(s, sh.red, red_phase, tot);
       const float mx = (float)(tot[0] / (double)nt), my = (float)(tot[1] / (double)nt);
       float mn_x = INFINITY, mn_y = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
       for (int i = tid; i < nt; i += nthr) {
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
         mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
       }
-      float *fr = reinterpret_cast<float *>(sh.red);
+      float *fr = sh.wred;
       if ((tid & 31) == 0) {
         fr[(tid >> 5) * 4 + 0] = mn_x, fr[(tid >> 5) * 4 + 1] = mn_y;
         fr[(tid >> 5) * 4 + 2] = mxx, fr[(tid >> 5) * 4 + 3] = mxy;
@@ -410,8 +430,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         n_fin += verdict;
         dist[i] = verdict ? max_d2 : INFINITY;  // upper bound of a finite point without candidate
       }
-      int total_fin;
-      block_exclusive_scan(n_fin, sh.scan, total_fin);  // (its barriers also publish dist[] / qstate[])
+      const int total_fin = block_total(n_fin, &sh.tot[0][0], tot_phase);  // (its barrier also publishes dist[] / qstate[])
       // pass C: settle what still matters
       if (!small) {
         float stop_d2 = INFINITY;
@@ -419,7 +438,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
           if (prm.trim_ratio < 1.0f && total_fin > 0) {
             int kk = (int)(size_t)__fmul_rn((float)total_fin, prm.trim_ratio);
             if (kk >= total_fin) kk = total_fin - 1;
-            stop_d2 = block_select_kth(dist, ns, kk, sh);  // kk-th smallest upper bound >= kk-th smallest distance
+            stop_d2 = block_select_kth(dist, ns, kk, sh, sel_pass);  // kk-th smallest upper bound >= kk-th smallest distance
           }
         } else if (prm.outlier_max_dist > 0.f) {
           stop_d2 = out_d2;
@@ -458,7 +477,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
             if (dist[i] < INFINITY) m = fmaxf(m, dist[i]);
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-          float *fr = reinterpret_cast<float *>(sh.red);
+          float *fr = sh.wred;
           if ((tid & 31) == 0) fr[tid >> 5] = m;
           __syncthreads();
           m = 0.f;
@@ -468,7 +487,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         } else {
           int kk = (int)(size_t)__fmul_rn((float)total_fin, prm.trim_ratio);
           if (kk >= total_fin) kk = total_fin - 1;
-          limit = block_select_kth(dist, ns, kk, sh);
+          limit = block_select_kth(dist, ns, kk, sh, sel_pass);
         }
       }
 
@@ -486,7 +505,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         const float2 r = sorted[match[i]];
         s5[0] += 1.0, s5[1] += (double)q.x, s5[2] += (double)q.y, s5[3] += (double)r.x, s5[4] += (double)r.y;
       }
-      block_sum<5>(s5, sh.red, t5);
+      block_sum<5>(s5, sh.red, red_phase, t5);
       const int n_keep = (int)t5[0];
       if (n_keep == 0) {
         if (tid == 0) sh.status = ICP_NO_POINT;
@@ -508,7 +527,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
         s4[0] += (double)__fmul_rn(qx, px), s4[1] += (double)__fmul_rn(qx, py);
         s4[2] += (double)__fmul_rn(qy, px), s4[3] += (double)__fmul_rn(qy, py);
       }
-      block_sum<4>(s4, sh.red, t4);
+      block_sum<4>(s4, sh.red, red_phase, t4);
 
       // 3e. rigid fit, T_iter update, checkers (one thread)
       if (tid == 0) {
@@ -659,7 +678,7 @@ __global__ void __launch_bounds__(ICP_THREADS) match_kernel(const MatchBatch b) 
 
 // ---------------------------------------------------------------------------- host side
 static int pick_max_cells(int nt_max) {
-  int c = 2 * nt_max;
+  int c = nt_max + nt_max / 2;  // the grid aims at one point per cell; the slack absorbs elongated bounding boxes
   if (c < 256) c = 256;
   if (c > GRID_MAX_CELLS) c = GRID_MAX_CELLS;
   return c;
@@ -677,6 +696,8 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   SFE_REQUIRE(nt_max <= 65535 && ns_max <= 65535, "icp: clouds of more than 65535 points are not supported (got %d, %d)",
               ns_max, nt_max);
   SFE_REQUIRE(prm->max_iterations >= 1, "icp: maxIterationCount must be >= 1");
+  SFE_REQUIRE(prm->smooth_length < ICP_HIST, "icp: smoothLength %d is not supported (at most %d)", prm->smooth_length,
+              ICP_HIST - 1);
   IcpBatch b{};
   b.src_pts = src_pts, b.src_off = src_off, b.tgt_pts = tgt_pts, b.tgt_off = tgt_off;
   b.src_cnt = src_cnt, b.tgt_cnt = tgt_cnt, b.min_points = min_points;
@@ -687,9 +708,15 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   b.max_cells = pick_max_cells(b.nt_max);
   b.cell_scale = 1.0f;
   b.prm = *prm;
-  size_t smem = ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
-                sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
-                sizeof(float) * (size_t)b.ns_max + 2 * sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 16;
+  auto smem_for = [&](int max_cells) {
+    return ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
+           sizeof(uint32_t) * (size_t)((max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
+           sizeof(float) * (size_t)b.ns_max + 2 * sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 16;
+  };
+  // big problems: trade cell-table entries (coarser cells) for room before giving up
+  while (smem_for(b.max_cells) > (size_t)ctx->max_smem_optin && b.max_cells > b.nt_max / 4 + 256)
+    b.max_cells -= b.max_cells / 8;
+  const size_t smem = smem_for(b.max_cells);
   if (smem > (size_t)ctx->max_smem_optin) {
     set_error("icp: source %d + target %d points need %zu B of shared memory per CTA (limit %d)", ns_max, nt_max, smem,
               ctx->max_smem_optin);
