@@ -174,19 +174,21 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
       const int t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
-    int run = incl - sum, bin = 255, kn = 0;
-    const bool mine = kk >= run && kk < incl;
-    if (mine) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (kk >= run && kk < run + c[j]) bin = lane * 8 + j, kn = kk - run;
-        run += c[j];
-      }
-    }
-    const unsigned owner = __ballot_sync(0xffffffffu, mine);
+    // the lane whose 8 bins contain rank kk, then lanes 0..7 look at those 8 bins together
+    const unsigned owner = __ballot_sync(0xffffffffu, kk >= incl - sum && kk < incl);
     const int src = owner ? __ffs(owner) - 1 : 31;
-    bin = __shfl_sync(0xffffffffu, bin, src);
-    kk = __shfl_sync(0xffffffffu, kn, src);
+    const int base = __shfl_sync(0xffffffffu, incl - sum, src);  // number of entries in the bins before lane src's
+    const int cj = hist[src * 8 + (lane & 7)];
+    int ij = cj;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, ij, d);
+      if ((lane & 7) >= d) ij += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, kk - base < ij) & 0xffu;
+    const int j = hit ? __ffs(hit) - 1 : 7;
+    const int bin = src * 8 + j;
+    kk = kk - base - (__shfl_sync(0xffffffffu, ij, j) - __shfl_sync(0xffffffffu, cj, j));
     prefix |= (uint32_t)bin << shift;
     mask |= 255u << shift;
   }
