@@ -25,6 +25,8 @@ constexpr int CLOUD_THREADS = 512;
 constexpr int DS_MAX_DEPTH = 15;
 constexpr int DS_FAST_DEPTH = 7;                 // 4^7 = 16384 leaves: counting-sort path
 constexpr int DS_FAST_CELLS = 1 << (2 * DS_FAST_DEPTH);
+constexpr int DS_WIDE_PREFIX = 6;                // deeper trees: 4^6 cells of the first six levels, 32-bit keys
+constexpr int DS_WIDE_CELLS = 1 << (2 * DS_WIDE_PREFIX);
 
 struct CloudBatch {
   const float *pts;  // [total][dim]
@@ -40,7 +42,7 @@ struct CloudBatch {
   unsigned long long *sort_ws;  // global sort buffer when n_pad does not fit shared memory
   uint16_t *orig_ws;
   int sort_in_smem;
-  int fast_ok;  // shared memory was sized for the counting-sort path
+  int smem_bytes;  // dynamic shared memory of the launch (the counting-sort path is taken by every cloud that fits)
 };
 
 __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBatch b) {
@@ -100,15 +102,25 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
     }
     __syncthreads();
     const int D = depth_s;
-    if (D <= DS_FAST_DEPTH && b.fast_ok) {
-      // ---- fast path: at most 4^7 leaves -> the path key indexes a table.  Counting sort by leaf (atomics;
-      //      members land in arbitrary order), then every leaf's members are put back in index order, which is
-      //      all the reference's member order is (a stable partition of the index list at every level).
-      uint16_t *key16 = reinterpret_cast<uint16_t *>(smem_raw);                                   // [n_max]
-      uint32_t *cellw = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(uint16_t) * (size_t)b.n_max + 15) & ~size_t(15)));
-      uint16_t *sidx = reinterpret_cast<uint16_t *>(cellw + DS_FAST_CELLS / 2 + 4);              // [n_max]
-      float *facc = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sidx) + ((sizeof(uint16_t) * (size_t)b.n_max + 15) & ~size_t(15)));
-      const int ncells = 1 << (2 * D), nwords = (ncells + 2) / 2;
+    const bool wide = D > DS_FAST_DEPTH;
+    const size_t a16 = (sizeof(uint16_t) * (size_t)n + 15) & ~size_t(15);  // layout sized by THIS cloud
+    const size_t need = (wide ? 2 * a16 : a16) + sizeof(uint32_t) * ((wide ? DS_WIDE_CELLS : DS_FAST_CELLS) / 2 + 4) +
+                        a16 + sizeof(float) * (size_t)n + 16;
+    if (n <= 65535 && need <= (size_t)b.smem_bytes) {
+      // ---- counting-sort path.  The first Dp levels of the path key index a table of cells (Dp = D up to 7
+      //      levels = 16384 leaves; deeper trees use 6 levels and finish inside the cell): counting sort by
+      //      cell with atomics (members land in arbitrary order), then every member finds its rank inside its
+      //      cell by (key, index) -- all members work in parallel -- which restores the reference's member order
+      //      (a stable partition of the index list at every level) and groups the leaves of a cell.
+      const int Dp = wide ? DS_WIDE_PREFIX : D;
+      const int sub_bits = 2 * (D - Dp);
+      uint16_t *key16 = reinterpret_cast<uint16_t *>(smem_raw);                        // [n_max] (D <= 7)
+      uint32_t *key32 = reinterpret_cast<uint32_t *>(smem_raw);                        // [n_max] (D > 7)
+      uint32_t *cellw = reinterpret_cast<uint32_t *>(smem_raw + (wide ? 2 * a16 : a16));
+      uint16_t *sidx = reinterpret_cast<uint16_t *>(cellw + (wide ? DS_WIDE_CELLS : DS_FAST_CELLS) / 2 + 4);  // [n_max]
+      float *facc = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sidx) + a16);
+      uint16_t *tmp = reinterpret_cast<uint16_t *>(facc);  // sorted member list before it replaces sidx
+      const int ncells = 1 << (2 * Dp), nwords = (ncells + 2) / 2;
       for (int w = tid; w < nwords; w += nthr) cellw[w] = 0;
       __syncthreads();
       for (int i = tid; i < n; i += nthr) {
@@ -122,11 +134,12 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
           cx = __fadd_rn(cx, (id & 1u) ? r : -r);
           cy = __fadd_rn(cy, (id & 2u) ? r : -r);
         }
-        key16[i] = (uint16_t)key;
-        atomicAdd(&cellw[key >> 1], (key & 1u) ? 0x10000u : 1u);
+        if (wide) key32[i] = key; else key16[i] = (uint16_t)key;
+        const unsigned cell = key >> sub_bits;
+        atomicAdd(&cellw[cell >> 1], (cell & 1u) ? 0x10000u : 1u);
       }
       __syncthreads();
-      {  // inclusive ends per leaf (two 16-bit counters per word)
+      {  // inclusive ends per cell (two 16-bit counters per word)
         const int per = (nwords + nthr - 1) / nthr;
         const int w0 = min(tid * per, nwords), w1 = min(w0 + per, nwords);
         int local = 0;
@@ -142,57 +155,99 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
       }
       __syncthreads();
       for (int i = tid; i < n; i += nthr) {
-        const unsigned key = key16[i];
-        const uint32_t old = atomicSub(&cellw[key >> 1], (key & 1u) ? 0x10000u : 1u);
-        sidx[(int)((key & 1u) ? (old >> 16) : (old & 0xffffu)) - 1] = (uint16_t)i;
+        const unsigned cell = (wide ? key32[i] : (unsigned)key16[i]) >> sub_bits;
+        const uint32_t old = atomicSub(&cellw[cell >> 1], (cell & 1u) ? 0x10000u : 1u);
+        sidx[(int)((cell & 1u) ? (old >> 16) : (old & 0xffffu)) - 1] = (uint16_t)i;
       }
       __syncthreads();
       const uint16_t *cstart = reinterpret_cast<const uint16_t *>(cellw);  // [ncells + 1], entry ncells == n
-      // members of every leaf back into index order (insertion sort; leaves are small)
-      for (int c = tid; c < ncells; c += nthr) {
-        const int s0 = cstart[c], e0 = cstart[c + 1];
-        for (int a = s0 + 1; a < e0; ++a) {
-          const uint16_t v = sidx[a];
-          int q = a - 1;
-          while (q >= s0 && sidx[q] > v) sidx[q + 1] = sidx[q], --q;
-          sidx[q + 1] = v;
+      // rank of every member inside its cell by (key, index)
+      for (int a = tid; a < n; a += nthr) {
+        const int ia = sidx[a];
+        const unsigned ka = wide ? key32[ia] : (unsigned)key16[ia];
+        const unsigned cell = ka >> sub_bits;
+        const int s0 = cstart[cell], e0 = cstart[cell + 1];
+        int rank = 0;
+        if (wide) {
+          for (int q = s0; q < e0; ++q) {
+            const int iq = sidx[q];
+            const unsigned kq = key32[iq];
+            rank += (kq < ka) || (kq == ka && iq < ia);
+          }
+        } else {
+          for (int q = s0; q < e0; ++q) rank += (int)sidx[q] < ia;
         }
+        tmp[s0 + rank] = (uint16_t)ia;
       }
+      __syncthreads();
+      for (int a = tid; a < n; a += nthr) sidx[a] = tmp[a];
       __syncthreads();
       // per member: float32 sum of distances to the members of its leaf, in member order
       for (int a = tid; a < n; a += nthr) {
         const int ia = sidx[a];
-        const unsigned key = key16[ia];
-        const int s0 = cstart[key], e0 = cstart[key + 1];
+        const unsigned ka = wide ? key32[ia] : (unsigned)key16[ia];
+        const unsigned cell = ka >> sub_bits;
+        int s0 = cstart[cell], e0 = cstart[cell + 1];
+        if (wide) {  // the leaf is the run of equal keys around a
+          int s = a, e = a + 1;
+          while (s > s0 && key32[sidx[s - 1]] == ka) --s;
+          while (e < e0 && key32[sidx[e]] == ka) ++e;
+          s0 = s, e0 = e;
+        }
         const float ax = pts[(size_t)ia * b.dim], ay = pts[(size_t)ia * b.dim + 1];
         float sum = 0.f;
-        for (int q = s0; q < e0; ++q) {
+        int q = s0;
+        for (; q + 4 <= e0; q += 4) {  // four members per trip: loads and square roots overlap, the sum stays in order
+          const int i0 = sidx[q], i1 = sidx[q + 1], i2 = sidx[q + 2], i3 = sidx[q + 3];
+          const float d0 = sqrtf(dist2_rn(ax - pts[(size_t)i0 * b.dim], ay - pts[(size_t)i0 * b.dim + 1]));
+          const float d1 = sqrtf(dist2_rn(ax - pts[(size_t)i1 * b.dim], ay - pts[(size_t)i1 * b.dim + 1]));
+          const float d2 = sqrtf(dist2_rn(ax - pts[(size_t)i2 * b.dim], ay - pts[(size_t)i2 * b.dim + 1]));
+          const float d3 = sqrtf(dist2_rn(ax - pts[(size_t)i3 * b.dim], ay - pts[(size_t)i3 * b.dim + 1]));
+          sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, d0), d1), d2), d3);
+        }
+        for (; q < e0; ++q) {
           const int iq = sidx[q];
           sum = __fadd_rn(sum, sqrtf(dist2_rn(ax - pts[(size_t)iq * b.dim], ay - pts[(size_t)iq * b.dim + 1])));
         }
         facc[a] = sum;
       }
       __syncthreads();
-      // leaves in key order (= depth-first order): every thread owns a contiguous run of leaves
+      // leaves in key order (= depth-first order): every thread owns a contiguous run of cells
       {
         const int per = (ncells + nthr - 1) / nthr;
         const int c0 = min(tid * per, ncells), c1 = min(c0 + per, ncells);
         int mine = 0;
-        for (int c = c0; c < c1; ++c) mine += cstart[c + 1] > cstart[c];
+        if (wide) {
+          for (int q = cstart[c0]; q < cstart[c1]; ++q)
+            mine += (q == cstart[c0]) || key32[sidx[q]] != key32[sidx[q - 1]];
+        } else {
+          for (int c = c0; c < c1; ++c) mine += cstart[c + 1] > cstart[c];
+        }
         int total;
         int rank = block_exclusive_scan(mine, scan, total);
-        for (int c = c0; c < c1; ++c) {
-          const int s0 = cstart[c], e0 = cstart[c + 1];
-          if (e0 <= s0) continue;
+        int q = cstart[c0];
+        const int qend = cstart[c1];
+        int c = c0;
+        while (q < qend) {
+          int e0;
+          if (wide) {
+            const unsigned kq = key32[sidx[q]];
+            e0 = q + 1;
+            while (e0 < qend && key32[sidx[e0]] == kq) ++e0;
+          } else {
+            while (cstart[c + 1] <= q) ++c;
+            e0 = cstart[c + 1];
+          }
           float best = 3.402823466e+38f;
-          int med = s0;
-          for (int q = s0; q < e0; ++q)
-            if (facc[q] < best) best = facc[q], med = q;
+          int med = q;
+          for (int m = q; m < e0; ++m)
+            if (facc[m] < best) best = facc[m], med = m;
           const int idx = sidx[med];
           const size_t dst = (size_t)(o + rank);
           for (int d = 0; d < b.dim; ++d) b.out_pts[dst * b.dim + d] = pts[(size_t)idx * b.dim + d];
           b.out_idx[dst] = idx;
           ++rank;
+          q = e0;
         }
         if (tid == 0) b.out_count[cl] = total;
       }
@@ -392,14 +447,16 @@ int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cn
   size_t smem = (b.sort_in_smem ? smem_sort : 0) + smem_acc;
   {
     const size_t a16 = (sizeof(uint16_t) * (size_t)b.n_max + 15) & ~size_t(15);
-    const size_t fast = a16 + sizeof(uint32_t) * (DS_FAST_CELLS / 2 + 4) + a16 + sizeof(float) * (size_t)b.n_max + 16;
-    b.fast_ok = b.n_max <= 65535 && fast <= (size_t)ctx->max_smem_optin - 4096;
-    if (b.fast_ok && fast > smem) smem = fast;
+    const size_t lay_a = a16 + sizeof(uint32_t) * (DS_FAST_CELLS / 2 + 4) + a16 + sizeof(float) * (size_t)b.n_max + 16;
+    const size_t lay_b = 2 * a16 + sizeof(uint32_t) * (DS_WIDE_CELLS / 2 + 4) + a16 + sizeof(float) * (size_t)b.n_max + 16;
+    const size_t fast = lay_a > lay_b ? lay_a : lay_b;
+    if (b.n_max <= 65535 && fast <= (size_t)ctx->max_smem_optin - 4096 && fast > smem) smem = fast;
   }
   if (smem > (size_t)ctx->max_smem_optin - 4096) {
     set_error("downsample: clouds of %d points are not supported (shared memory)", n_max);
     return SFE_ERR_UNSUPPORTED;
   }
+  b.smem_bytes = (int)smem;
   SFE_CUDA(cudaFuncSetAttribute(downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, downsample_kernel, CLOUD_THREADS, smem));
