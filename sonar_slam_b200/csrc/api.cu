@@ -200,7 +200,8 @@ int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int
 int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
             const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
             const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,
-            int *inliers, int *status, const int *raw_cnt = nullptr, int raw_cap = 0);
+            int *inliers, int *status, const int *raw_cnt = nullptr, int raw_cap = 0, int class_mode = 0,
+            int class_ns = 0, int class_nt = 0, int force_threads = 0);
 int match_run(sfe_ctx *ctx, const float *ref_pts, const int *ref_off, const float *in_pts, const int *in_off, int P,
               int nt_max, float max_dist, int32_t *ids, float *dists);
 

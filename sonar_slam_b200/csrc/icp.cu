@@ -39,6 +39,10 @@ struct IcpBatch {
   int min_points;      // problems whose source or target has fewer points are skipped (ICP_SKIPPED)
   const int *raw_cnt;  // optional: un-clamped size of the source's raw cloud; > raw_cap -> ICP_TOO_LARGE
   int raw_cap;
+  // size classes: a batch can be served by two launches with different shared-memory footprints.
+  //   1: this launch only takes problems that fit (ns <= ns_max, nt <= nt_max) and leaves the others untouched;
+  //   2: this launch skips the problems with ns <= class_ns and nt <= class_nt (the other launch's share)
+  int class_mode, class_ns, class_nt;
   const int *src_id;  // may be null (problem p uses source p)
   const int *tgt_id;  // may be null
   const float *guess; // [P][9] row-major 3x3
@@ -232,6 +236,8 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
     const float *tgt = b.tgt_pts + 2 * (size_t)b.tgt_off[ti];
     const int nt = b.tgt_cnt ? b.tgt_cnt[ti] : b.tgt_off[ti + 1] - b.tgt_off[ti];
     const float *guess = b.guess + 9 * (size_t)p;
+    if (b.class_mode == 1 && (ns > b.ns_max || nt > b.nt_max)) continue;
+    if (b.class_mode == 2 && ns <= b.class_ns && nt <= b.class_nt) continue;
     __syncthreads();  // previous problem fully retired before shared state is reused
 
     // ---- admission checks (thread 0), failure leaves T = guess
@@ -689,7 +695,8 @@ static int pick_max_cells(int nt_max) {
 int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
             const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
             const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,
-            int *inliers, int *status, const int *raw_cnt, int raw_cap) {
+            int *inliers, int *status, const int *raw_cnt, int raw_cap, int class_mode, int class_ns, int class_nt,
+            int force_threads) {
   SFE_REQUIRE(ctx && prm, "icp: null context or parameters");
   SFE_REQUIRE(P >= 0 && ns_max >= 0 && nt_max >= 0, "icp: negative sizes");
   if (P == 0) return SFE_OK;
@@ -704,6 +711,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   b.src_pts = src_pts, b.src_off = src_off, b.tgt_pts = tgt_pts, b.tgt_off = tgt_off;
   b.src_cnt = src_cnt, b.tgt_cnt = tgt_cnt, b.min_points = min_points;
   b.raw_cnt = raw_cnt, b.raw_cap = raw_cap;
+  b.class_mode = class_mode, b.class_ns = class_ns, b.class_nt = class_nt;
   b.src_id = src_id, b.tgt_id = tgt_id, b.guess = guess;
   b.T_out = T_out, b.iters = iters, b.inliers = inliers, b.status = status;
   b.P = P, b.ns_max = ns_max > 0 ? ns_max : 1, b.nt_max = nt_max > 0 ? nt_max : 1;
@@ -726,15 +734,25 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   }
   // CTA size follows the source size (one NN query per thread and iteration is the sweet spot)
   // (measured on the config-4 replay: 256 threads beat 128 and 512 for ~360-point sources)
-  const int threads = b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS);
+  const int threads = force_threads > 0 ? force_threads : (b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS));
   // the attribute / occupancy queries are cached per (smem, threads): the front end calls this per copy chunk
-  static thread_local size_t c_smem = 0;
-  static thread_local int c_threads = 0, c_per_sm = 0, c_dev = -1;
-  if (c_smem != smem || c_threads != threads || c_dev != ctx->device) {
+  struct OccEntry { size_t smem; int threads, per_sm, dev; };
+  static thread_local OccEntry occ[4] = {};
+  static thread_local size_t attr_smem = 0;
+  static thread_local int attr_dev = -1, occ_next = 0;
+  if (attr_dev != ctx->device || smem > attr_smem) {
     SFE_CUDA(cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem, attr_dev = ctx->device;
+  }
+  int c_per_sm = 0;
+  for (const OccEntry &e : occ)
+    if (e.per_sm > 0 && e.smem == smem && e.threads == threads && e.dev == ctx->device) c_per_sm = e.per_sm;
+  if (c_per_sm == 0) {
     int q = 1;
     SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, icp_kernel, threads, smem));
-    c_smem = smem, c_threads = threads, c_per_sm = q < 1 ? 1 : q, c_dev = ctx->device;
+    c_per_sm = q < 1 ? 1 : q;
+    occ[occ_next] = OccEntry{smem, threads, c_per_sm, ctx->device};
+    occ_next = (occ_next + 1) % 4;
   }
   const int per_sm = c_per_sm;
   int grid = ctx->sm_count * per_sm;

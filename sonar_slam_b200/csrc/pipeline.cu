@@ -29,7 +29,15 @@ int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int
 int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
             const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
             const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,
-            int *inliers, int *status, const int *raw_cnt = nullptr, int raw_cap = 0);
+            int *inliers, int *status, const int *raw_cnt = nullptr, int raw_cap = 0, int class_mode = 0,
+            int class_ns = 0, int class_nt = 0, int force_threads = 0);
+
+// Size class of the first ICP launch (fe_match).  Measured on the config-4 replay (filtered clouds: median 326,
+// max 639 points; window submaps <= 1808 raw points): one launch sized for the capacities (1024 / 3072, 4 CTAs per
+// SM) 2.40 ms per 4096 frames with 256 threads, 2.59 ms with 128; this class with 128 threads (6 CTAs per SM) 2.11 ms;
+// a class that leaves 14 % of the frames to the second launch (512 points) 3.11 ms -- the tail of a nearly empty
+// launch costs a full problem latency.
+constexpr int FE_ICP_SMALL_SRC = 640, FE_ICP_SMALL_TGT = 1536, FE_ICP_SMALL_THREADS = 128;
 
 // T_ab = pose_a^-1 * pose_b as float32 3x3 (gtsam Pose2::between, then matrix().astype(float32)).
 // Evaluated on the host in double (libm), so the float32 matrices the kernels see are the ones a
@@ -353,9 +361,20 @@ static int fe_match(sfe_frontend *fe, int f0, int n) {
   }
   fe_toc(fe);
   fe_tic(fe, SFE_FE_ICP);
+  // Two launches by problem size: a sonar frame's filtered cloud is a few hundred points, far below the
+  // capacities the buffers are sized for, and the ICP kernel's occupancy is set by its shared-memory footprint.
+  // The first launch is sized for the common case (6 CTAs per SM instead of 4) and leaves bigger problems
+  // untouched; the second, sized for the capacities, only takes those.
+  const int ns_small = p.cap_source < FE_ICP_SMALL_SRC ? p.cap_source : FE_ICP_SMALL_SRC;
+  const int nt_small = p.cap_target < FE_ICP_SMALL_TGT ? p.cap_target : FE_ICP_SMALL_TGT;
   int rc = icp_run(ctx, &p.icp, cloud, fe->off_pts + f0, cnt + f0, tgt, fe->off_tgt + f0, tcnt + f0, p.min_points,
-                   nullptr, nullptr, n, p.cap_source, p.cap_target, fe->guess + 9 * (size_t)f0, fe->T + 9 * (size_t)f0,
-                   fe->iters + f0, fe->inliers + f0, fe->status + f0, fe->cnt_a + f0, cap);
+                   nullptr, nullptr, n, ns_small, nt_small, fe->guess + 9 * (size_t)f0, fe->T + 9 * (size_t)f0,
+                   fe->iters + f0, fe->inliers + f0, fe->status + f0, fe->cnt_a + f0, cap, 1, 0, 0, FE_ICP_SMALL_THREADS);
+  if (rc == SFE_OK && (ns_small < p.cap_source || nt_small < p.cap_target))
+    rc = icp_run(ctx, &p.icp, cloud, fe->off_pts + f0, cnt + f0, tgt, fe->off_tgt + f0, tcnt + f0, p.min_points,
+                 nullptr, nullptr, n, p.cap_source, p.cap_target, fe->guess + 9 * (size_t)f0,
+                 fe->T + 9 * (size_t)f0, fe->iters + f0, fe->inliers + f0, fe->status + f0, fe->cnt_a + f0, cap, 2,
+                 ns_small, nt_small);
   fe_toc(fe);
   return rc;
 }

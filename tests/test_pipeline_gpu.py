@@ -51,3 +51,28 @@ def test_frontend_host_call_equals_oracle_chain(gpu_ctx, mode):
     for k in ("status", "iterations", "inliers", "npoints"):
         assert np.array_equal(again[k], got[k])
     assert np.array_equal(again["T"], got["T"])
+
+
+def test_frontend_both_icp_size_classes(gpu_ctx):
+    """The front end serves ICP with two launches by problem size (pipeline.cu: FE_ICP_SMALL_*).  A finer voxel
+    grid gives clouds on both sides of the 640-point class boundary; every frame must still equal the oracle."""
+    n = 10
+    d = synth.make_trajectory_frames(n, seed=5)
+    frames, poses = d["frames"].numpy(), d["poses_odom"]
+    geo = featx_ref.Geometry(30.0 / 512, 512, d["bearings"])
+    maps = _lib.Maps(gpu_ctx, geo.map_x, geo.map_y, 512, 512, geo.width, geo.height)
+    prm = dict(smooth_length=0, max_iterations=20)
+    fe = pipeline.FrontEnd(gpu_ctx, maps, max_frames=16, icp=_lib.IcpParams(**prm), min_points=30, resolution=0.35,
+                           submap_resolution=0.35, cap_source=4096, cap_target=12288)
+    got = fe.run_host(frames, poses, chunk_frames=4)
+    clouds, want = pipeline_ref.run(frames, poses, geo, min_points=30, submap_resolution=0.35,
+                                    icp_params=orc.IcpParams(**prm), resolution=0.35)
+    sizes = np.array([len(c) for c in clouds])
+    assert np.array_equal(got["npoints"], sizes)
+    assert (sizes > 640).any() and (sizes <= 640).any(), sizes  # both launches had work
+    for i in range(n):
+        assert got["status"][i] == want[i]["status"], (i, got["status"][i], want[i]["status"])
+        if want[i]["status"] == 0:
+            assert got["iterations"][i] == want[i]["iterations"] and got["inliers"][i] == want[i]["inliers"], i
+            dlt = np.abs(_pose(got["T"][i]) - _pose(want[i]["T"]))
+            assert dlt[:2].max() < 1e-3 and dlt[2] < 1e-3, (i, dlt)
