@@ -97,9 +97,6 @@ class FeatureExtraction(object):
         self.outlier_filter_min_points = fl.get("min_points", self.outlier_filter_min_points)
         self.skip = fl.get("skip", self.skip)
         self.compressed_images = params.get("compressed_images", False)
-        if self.compressed_images:
-            raise NotImplementedError("compressed pings (cv2.imdecode, feature_extraction.py:210-213) are outside "
-                                      "this library's scope: pass decoded uint8 images")
         self.configure()
 
     def generate_map_xy(self, ping):
@@ -141,16 +138,31 @@ class FeatureExtraction(object):
         self.points = points
         return points
 
+    def ping_image(self, sonar_msg):
+        """The polar uint8 image of a ping.  Compressed pings (`compressed_images: True`, a sensor_msgs/CompressedImage
+        whose `.data` holds the PNG/JPEG bytes) are decoded on the host exactly like the reference does
+        (feature_extraction.py:210-213: cv2.imdecode as BGR, then BGR -> gray); anything else is taken as the decoded
+        [num_ranges, num_beams] array (the reference's ros_numpy.image_to_numpy branch, :217)."""
+        img = getattr(sonar_msg, "image", None)
+        if img is None:
+            img = sonar_msg.ping
+        data = getattr(img, "data", None)
+        if self.compressed_images and isinstance(data, (bytes, bytearray, memoryview)):
+            import cv2  # the reference's own decoder; only needed for compressed bags
+            buf = np.frombuffer(data, np.uint8)
+            dec = cv2.imdecode(buf, cv2.IMREAD_COLOR)
+            if dec is None:
+                raise ValueError("FeatureExtraction: the compressed ping could not be decoded")
+            img = cv2.cvtColor(np.array(dec).astype(np.uint8), cv2.COLOR_BGR2GRAY)
+        return np.ascontiguousarray(img)
+
     def callback(self, sonar_msg):
         if sonar_msg.ping_id % self.skip != 0:
             self.feature_img = None
             nan = np.array([[np.nan, np.nan]])
             return self.publish_features(sonar_msg, nan)
 
-        img = getattr(sonar_msg, "image", None)
-        if img is None:
-            img = sonar_msg.ping
-        img = np.ascontiguousarray(img)
+        img = self.ping_image(sonar_msg)
         if img.dtype != np.uint8 or img.ndim != 2:
             raise TypeError("FeatureExtraction.callback: the ping image must be uint8 [num_ranges, num_beams]")
         self.generate_map_xy(sonar_msg)

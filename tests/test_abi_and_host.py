@@ -69,3 +69,25 @@ def test_cfar_module_argument_checks_happen_before_any_device_work():
         cfar.os(img, 20, 5, 10.0, 1.0)                  # rank=None -> Ntc/2 float (CFAR.py:24) is rejected too
     with pytest.raises(TypeError):
         cfar.ca(np.zeros((4, 4), dtype=complex), 1, 1, 1.0)
+
+
+def test_compressed_ping_is_decoded_like_the_reference():
+    """feature_extraction.py:210-213: cv2.imdecode(..., IMREAD_COLOR) then BGR -> gray; PNG is lossless, so the decoded
+    ping equals the raw one; the uncompressed branch passes arrays through."""
+    import types
+    cv2 = pytest.importorskip("cv2")
+    from sonar_slam_b200 import synth
+    from sonar_slam_b200.bruce_slam.feature_extraction import FeatureExtraction
+    img = synth.make_frame(seed=1)
+    ok, png = cv2.imencode(".png", img)
+    assert ok
+    fe = FeatureExtraction()
+    fe.compressed_images = True
+    got = fe.ping_image(types.SimpleNamespace(ping=types.SimpleNamespace(data=png.tobytes())))
+    want = cv2.cvtColor(np.array(cv2.imdecode(np.frombuffer(png.tobytes(), np.uint8), cv2.IMREAD_COLOR)).astype(np.uint8),
+                        cv2.COLOR_BGR2GRAY)
+    assert got.dtype == np.uint8 and np.array_equal(got, want) and np.array_equal(got, img)
+    with pytest.raises(ValueError):
+        fe.ping_image(types.SimpleNamespace(ping=types.SimpleNamespace(data=b"not an image")))
+    fe.compressed_images = False
+    assert np.array_equal(fe.ping_image(types.SimpleNamespace(ping=img)), img)
