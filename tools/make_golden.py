@@ -22,6 +22,11 @@ Fixtures written:
   tests/golden/featx_config1.npz    FeatureExtraction.callback on the config-1 ping:
                                     map_x/map_y digests + samples, Cartesian (row,col)
                                     list and the metric points it publishes
+  tests/golden/slam_host.npz        host-side numpy logic of SLAM.get_points (slam.py:229-292),
+                                    SLAM.get_overlap (:389-424) and SLAM.compute_icp_with_cov
+                                    (:325-387) run unmodified, with bruce_slam.pcl.{downsample,match}
+                                    served by the CPU oracle and ICP.compute returning preset
+                                    transforms (the natives themselves are covered elsewhere)
   tests/golden/globalinit.npz       SLAM.get_matching_cost_subroutine1 (slam.py:461-570) run
                                     unmodified on a synthetic source/target pair: the dilated
                                     target grid (packed) and the cost of 96 candidate poses.
@@ -81,7 +86,20 @@ def _install_gtsam_stub():
 
     g = _StubModule("gtsam")
     g.__path__ = []
-    g.Pose2 = globalinit_ref.Pose2
+    class Pose2(globalinit_ref.Pose2):  # + the accessor compute_icp_with_cov uses (slam.py:377)
+        def rotation(self):
+            R = self.matrix()[:2, :2]
+            return types.SimpleNamespace(matrix=lambda: R)
+
+        def compose(self, other):
+            o = globalinit_ref.Pose2.compose(self, other)
+            return Pose2(o.x(), o.y(), o.theta())
+
+        def between(self, other):
+            o = globalinit_ref.Pose2.between(self, other)
+            return Pose2(o.x(), o.y(), o.theta())
+
+    g.Pose2 = Pose2
     for name in ("Rot3", "Pose3"):  # conversions.g2n does isinstance() against these
         setattr(g, name, type(name, (), {}))
     g.Point2 = lambda *a: np.zeros(2)
@@ -224,6 +242,69 @@ def main():
               xs=xs, costs=costs, pose_samples=np.array(pose_samples), grid_shape=np.array(grid.shape, np.int64),
               grid_packed=np.packbits(grid > 0), grid_sha256=np.array(_digest(grid)))
     np.savez_compressed(os.path.join(out, "globalinit.npz"), **gi)
+    # ---- host-side logic of get_points / get_overlap / compute_icp_with_cov ----------
+    from oracle import oracle as orc
+    pcl_stub = sys.modules["bruce_slam.pcl"]
+
+    def _downsample(points, *rest):  # both pybind overloads (pcl.cpp:128,143), arithmetic = CPU oracle
+        if len(rest) == 1:
+            out, _ = orc.downsample(np.asarray(points, np.float32), rest[0])
+            return out
+        desc, res = rest
+        out, idx = orc.downsample(np.asarray(points, np.float32), res)
+        return out, np.asarray(desc)[idx]
+
+    def _match(ref, pts, knn, max_dist):
+        assert knn == 1
+        return orc.match(np.asarray(ref, np.float32), np.asarray(pts, np.float32), max_dist)
+
+    pcl_stub.downsample, pcl_stub.match = _downsample, _match
+    rng = np.random.default_rng(5)
+    kfs, kf_arrays = [], {}
+    for k in range(4):
+        c, _, _ = synth.make_icp_pair(30 + k, n_source=300 + 40 * k, n_target=400, extent=30.0, sensor_range=15.0)
+        pose = gtsam.Pose2(0.4 * k, -0.2 * k, 0.05 * k)
+        kf = types.SimpleNamespace(points=c, pose=pose, transf_points=slam_mod.Keyframe.transform_points(c, pose))
+        kfs.append(kf)
+        kf_arrays[f"kf{k}_points"] = c
+        kf_arrays[f"kf{k}_pose"] = np.array([pose.x(), pose.y(), pose.theta()])
+    fake = types.SimpleNamespace(current_key=4, keyframes=kfs, point_resolution=0.5, point_noise=0.5,
+                                 icp_odom_sigmas=np.array([0.1, 0.1, 0.01]))
+    S = slam_mod.SLAM
+    sh = dict(kf_arrays)
+    sh["points_all"] = S.get_points(fake)
+    sh["points_ref_idx"] = S.get_points(fake, [0, 1, 2], 3)
+    sh["points_ref_pose"] = S.get_points(fake, [1, 3], gtsam.Pose2(1.0, 0.5, -0.2))
+    pk, kk = S.get_points(fake, [0, 2, 3], 1, True)
+    sh["points_keys_pts"], sh["points_keys_keys"] = pk, kk
+    n_ov, ind = S.get_overlap(fake, kfs[1].points, kfs[2].points, kfs[1].pose, kfs[2].pose, True)
+    sh["overlap_count"], sh["overlap_indices"] = np.int64(n_ov), ind
+    sh["overlap_plain"] = np.int64(S.get_overlap(fake, kfs[0].points, kfs[3].points))
+    # compute_icp_with_cov: 14 guesses, ICP answers preset (3 failures); MinCovDet draws from numpy's global RNG
+    Ts = []
+    for i in range(14):
+        th = 0.03 + rng.normal(0, 0.004)
+        T = np.array([[np.cos(th), -np.sin(th), 0.5 + rng.normal(0, 0.02)],
+                      [np.sin(th), np.cos(th), -0.3 + rng.normal(0, 0.02)], [0, 0, 1]], np.float32)
+        if i == 4:
+            T[0, 2] += 0.8  # an outlier the robust estimate should ignore
+        Ts.append(("success" if i not in (2, 7, 11) else "ErrorMnimizer: no point to minimize", T))
+    calls = iter(Ts)
+    fake.icp = types.SimpleNamespace(compute=lambda s_, t_, g_: next(calls))
+    guesses = [gtsam.Pose2(0.01 * i, 0.0, 0.0) for i in range(14)]
+    np.random.seed(1234)
+    msg, m, cov, samples = S.compute_icp_with_cov(fake, kfs[0].points, kfs[1].points, guesses)
+    sh["cov_T"] = np.array([t for _, t in Ts])
+    sh["cov_ok"] = np.array([m_ == "success" for m_, _ in Ts])
+    sh["cov_msg"] = np.array(msg)
+    sh["cov_mean"] = np.array([m.x(), m.y(), m.theta()])
+    sh["cov_cov"], sh["cov_samples"] = cov, samples
+    calls = iter(Ts[:5])  # four successes: below the five the reference asks for (slam.py:362-363)
+    msg2 = S.compute_icp_with_cov(fake, kfs[0].points, kfs[1].points, guesses[:5])
+    sh["cov_few_msg"] = np.array(msg2[0])
+    np.savez_compressed(os.path.join(out, "slam_host.npz"), **sh)
+    print("slam_host: all", sh["points_all"].shape, "keys", pk.shape, kk.shape, "overlap", int(n_ov), "cov msg", msg,
+          "mean", sh["cov_mean"], "few:", msg2[0])
     print("globalinit: grid", grid.shape, "occupied", int((grid > 0).sum()), "costs", costs[:6], "min", costs.min())
     print("golden fixtures written to", out)
 
