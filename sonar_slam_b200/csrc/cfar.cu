@@ -7,10 +7,11 @@
 //
 //  cfar_ring_tma_kernel   the streaming path for the shipped configuration
 //      (train_hs = 20, guard_hs = 5; CA / SOCA / GOCA).  One CTA owns a strip of
-//      128 beams of one frame and marches down the range axis once.  A producer
-//      warp streams [16 range bins x 128 beams] boxes of the frame through a
-//      4-stage shared-memory ring with TMA (cp.async.bulk.tensor + mbarrier);
-//      each of the 128 consumer threads owns ONE beam, reads every cell of its
+//      128 beams of one frame and marches down the range axis once.  [16 range
+//      bins x 128 beams] boxes of the frame stream through a 4-stage
+//      shared-memory ring with TMA (cp.async.bulk.tensor + mbarrier), refilled by
+//      one thread after every block's barrier (no producer warp: cfar_refill);
+//      each of the 128 threads owns ONE beam, reads every cell of its
 //      beam exactly once from shared memory and keeps the last 32 cells and the
 //      last 32 window sums in two register rings.  With W[i] = sum of the 20
 //      cells ending at range bin i, the lagging window of the cell under test r

@@ -96,8 +96,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
-// expires) instead of spinning -- a spinning producer warp was costing ~1/3 of the issue slots (ncu).
+// try_wait with a suspend-time hint: a waiting thread may sleep in hardware until the phase completes (or the
+// hint expires) instead of spinning on the barrier.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
