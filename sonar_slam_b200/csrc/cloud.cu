@@ -11,11 +11,13 @@
 // downsample: the quadtree is never materialised.  Splitting always halves the bounding square,
 //   so the leaf a point falls into at the size-limited depth D is found by D comparisons against
 //   centres computed with the same float32 additions the tree would use; the 2-bit child ids along
-//   the path form a key whose ascending order is the tree's depth-first visiting order.  Sorting
-//   (key, index) pairs with an in-CTA bitonic sort therefore groups points by leaf in output order
-//   with members in index order; nodes that the reference stops splitting early because they hold a
-//   single point produce the same groups.  Each group then picks its medoid (float32 sequential sum
-//   of Euclidean distances, first minimum wins).
+//   the path form a key whose ascending order is the tree's depth-first visiting order.  Grouping the
+//   points by key with members in index order therefore reproduces the tree's leaves in output order
+//   (nodes that the reference stops splitting early because they hold a single point produce the same
+//   groups).  The grouping is a counting sort by the first levels of the key in shared memory followed by
+//   a parallel rank inside each cell (taken by every cloud whose layout fits the launch's shared memory),
+//   or an in-CTA bitonic sort of (key, index) pairs for very large clouds.  Each group then picks its
+//   medoid (float32 sequential sum of Euclidean distances, first minimum wins).
 // remove_outlier: counts neighbours within the radius on the shared-memory grid of grid.cuh.
 #include "grid.cuh"
 

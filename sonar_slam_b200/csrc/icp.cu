@@ -10,7 +10,8 @@
 // One CTA solves one (source, target, guess) problem end to end: the target is centred on its
 // mean and counting-sorted into a uniform grid held in shared memory (grid.cuh), the source is
 // moved into the centred frame once, and every iteration runs entirely on chip:
-//   transform + grid NN search per source point  ->  exact k-th smallest distance (4-pass radix
+//   transform + grid NN search per source point (seeded with the previous iteration's match: only the
+//   cells overlapping the seed's disc are scanned)  ->  exact k-th smallest distance (4-pass radix
 //   select on the float bits)  ->  0/1 weights  ->  warp-shuffle / shared-memory reductions of the
 //   weighted means and the 2x2 cross-covariance (float32 products, float64 accumulation, fixed
 //   order: deterministic)  ->  closed-form 2-D rotation and translation, T_iter update and the
