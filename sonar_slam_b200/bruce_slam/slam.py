@@ -7,8 +7,6 @@ The pose-graph part of SLAM (ISAM2, PCM, keyframe logic) is out of this library'
 with the caller; `Pose2` below is a minimal stand-in for gtsam.Pose2 (x, y, theta, matrix,
 between, compose) used when gtsam is not importable.
 """
-import time as time_pkg
-
 import numpy as np
 
 from . import pcl

@@ -14,7 +14,7 @@ every test / bench input is generated here:
                           2-D wall scene, (source, target, ground truth) scan pairs
   make_trajectory_frames  frames seen from a moving vehicle (pipeline replay)
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 

@@ -1,6 +1,5 @@
 """CPU-only: the C-ABI library loads and exports what include/sonarfe.h declares; host-side
 logic of the drop-in classes (no compute calls -- there is no GPU here)."""
-import ctypes
 import json
 import os
 import re

@@ -3,8 +3,6 @@ import json
 import subprocess
 import sys
 
-import numpy as np
-
 
 def test_cpu_pipeline_leg_runs_on_a_tiny_sample():
     import bench

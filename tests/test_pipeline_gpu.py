@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import featx_ref, oracle as orc, pipeline_ref
-from sonar_slam_b200 import _lib, ops, pipeline, synth
+from sonar_slam_b200 import _lib, pipeline, synth
 
 pytestmark = pytest.mark.gpu
 

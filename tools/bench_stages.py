@@ -1,5 +1,5 @@
 """Per-stage timings of the front end on synthetic data (development aid, not the bench contract)."""
-import sys, time
+import sys
 import numpy as np
 import torch
 from sonar_slam_b200 import _lib, ops, synth

@@ -1,4 +1,4 @@
-import sys, numpy as np, torch
+import numpy as np, torch
 from sonar_slam_b200 import _lib, ops, synth
 P = 148
 pairs = [synth.make_icp_pair(s)[:2] for s in range(4)]
