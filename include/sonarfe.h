@@ -105,6 +105,14 @@ SFE_API int sfe_cfar_host(sfe_ctx *ctx, const void *img_host, int dtype, int n_f
 typedef struct sfe_maps sfe_maps;
 SFE_API int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_host, int rows, int cols, int R,
                             int B, double width, double height, sfe_maps **out);
+/* Diagnostic, host only (no context, no GPU): the inverse lists sfe_maps_create uploads -- for every polar cell
+ * the Cartesian pixels the detection-driven kernel tests when that cell is a detection -- as a CSR structure:
+ * off_out [R*B + 1], idx_out [*n_entries] pixel indices (row * cols + col).  A pixel is listed under the smallest
+ * set of its taps that every firing configuration must light (see featx.cu: build_inverse_lists).  Returns
+ * SFE_ERR_CAPACITY (with *n_entries set) when idx_capacity is too small. */
+SFE_API int sfe_maps_inverse_lists_host(const float *map_x_host, const float *map_y_host, int rows, int cols, int R,
+                                        int B, int32_t *off_out, int32_t *idx_out, int64_t idx_capacity,
+                                        int64_t *n_entries);
 SFE_API void sfe_maps_destroy(sfe_maps *maps);
 
 /* For each of n_frames polar 0/1 masks (bytes [n_frames][R][B], or the bit plane written by

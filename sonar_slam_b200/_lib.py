@@ -72,6 +72,8 @@ def _type_more(lib):
 
 
 _EXTRA_SIGNATURES = {
+    "sfe_maps_inverse_lists_host": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)],
     "sfe_costmap_create": [c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int, c_int, c_int, c_void_p,
                            c_void_p, ctypes.POINTER(c_void_p)],
     "sfe_costmap_grid_host": [c_void_p, c_void_p, c_void_p],
@@ -212,6 +214,22 @@ class Maps:
             self.close()
         except Exception:
             pass
+
+
+def inverse_lists(map_x, map_y, R, B):
+    """Host-only diagnostic (no GPU needed): the CSR inverse lists (polar cell -> Cartesian pixels to test) that
+    sfe_maps_create uploads for these sampling maps.  Returns (off int32 [R*B+1], idx int32 [n])."""
+    lib = load()
+    map_x = np.ascontiguousarray(map_x, np.float32)
+    map_y = np.ascontiguousarray(map_y, np.float32)
+    rows, cols = map_x.shape
+    off = np.empty(R * B + 1, np.int32)
+    cap = 4 * rows * cols
+    idx = np.empty(cap, np.int32)
+    n = ctypes.c_int64(0)
+    check(lib.sfe_maps_inverse_lists_host(ptr(map_x), ptr(map_y), rows, cols, int(R), int(B), ptr(off), ptr(idx), cap,
+                                          ctypes.byref(n)), "sfe_maps_inverse_lists_host")
+    return off, idx[: n.value].copy()
 
 
 def ellipse_spans(hs):

@@ -402,22 +402,12 @@ int cart_points_run(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const 
   return rc;
 }
 
-}  // namespace sfe
-
-using namespace sfe;
-
-extern "C" {
-
-int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_host, int rows, int cols, int R, int B,
-                    double width, double height, sfe_maps **out) {
-  SFE_REQUIRE(ctx && out, "sfe_maps_create: null context or out pointer");
-  *out = nullptr;
-  SFE_REQUIRE(map_x_host && map_y_host, "sfe_maps_create: null map pointer");
-  SFE_REQUIRE(rows > 0 && cols > 0 && R > 0 && B > 0, "sfe_maps_create: non-positive shape");
-  SFE_REQUIRE((long long)rows * cols < (1ll << 31), "sfe_maps_create: Cartesian image too large");
-  SFE_CUDA(cudaSetDevice(ctx->device));
+// ---------------------------------------------------------------------------- host side: per-geometry tables
+// cv2.remap's fixed-point sampling position of every Cartesian pixel (see cart_pixel_fires)
+static void build_map_table(const float *map_x_host, const float *map_y_host, int rows, int cols, int R, int B,
+                            std::vector<MapEntry> &tab) {
   const size_t n = (size_t)rows * cols;
-  std::vector<MapEntry> tab(n);
+  tab.assign(n, MapEntry{});
   for (size_t p = 0; p < n; ++p) {
     MapEntry e{};
     const float mx = map_x_host[p] * 32.0f, my = map_y_host[p] * 32.0f;
@@ -436,24 +426,65 @@ int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_ho
     }
     tab[p] = e;
   }
-  // inverse lists: polar cell -> Cartesian pixels that sample it with non-zero weight
-  std::vector<int32_t> inv_off((size_t)R * B + 1, 0);
+}
+
+// Inverse lists: polar cell -> Cartesian pixels the detection-driven kernel must test when that cell is a
+// detection.  A pixel fires iff the weights of its lit taps add up to >= 512 (of 1024), so it need not be listed
+// under every tap: taking its in-image taps by decreasing weight until the REMAINING ones together weigh less than
+// 512 gives a set S such that every firing configuration lights a tap of S (if none is lit, the lit taps are among
+// the remaining ones and cannot reach 512).  The kernel tests each listed candidate with the full rule, so the
+// result is unchanged while the lists shrink from ~3.9 to ~1.4 entries per pixel (625 of the 1024 (fx, fy)
+// fractions have one dominant tap).  Checked by enumeration and against cv2.remap in tests/test_oracle_featx.py.
+static void build_inverse_lists(const std::vector<MapEntry> &tab, int R, int B, std::vector<int32_t> &inv_off,
+                                std::vector<int32_t> &inv_idx) {
+  const size_t n = tab.size();
+  inv_off.assign((size_t)R * B + 1, 0);
   auto each_tap = [&](size_t p, auto &&fn) {
     const MapEntry &e = tab[p];
     if (!(e.flags & 1)) return;
-    const int wts[4] = {(32 - e.fx) * (32 - e.fy), e.fx * (32 - e.fy), (32 - e.fx) * e.fy, e.fx * e.fy};
+    int w[4] = {(32 - e.fx) * (32 - e.fy), e.fx * (32 - e.fy), (32 - e.fx) * e.fy, e.fx * e.fy};
+    int rest = 0;
     for (int t = 0; t < 4; ++t) {
       const int x = e.ix + (t & 1), y = e.iy + (t >> 1);
-      if (wts[t] > 0 && x >= 0 && x < B && y >= 0 && y < R) fn((size_t)y * B + x);
+      if (!(x >= 0 && x < B && y >= 0 && y < R)) w[t] = 0;  // out-of-image taps never contribute
+      rest += w[t];
+    }
+    while (rest >= 512) {
+      int best = 0;
+      for (int t = 1; t < 4; ++t)
+        if (w[t] > w[best]) best = t;  // largest remaining weight, lowest tap on ties
+      if (w[best] == 0) break;
+      fn((size_t)(e.iy + (best >> 1)) * B + (size_t)(e.ix + (best & 1)));
+      rest -= w[best];
+      w[best] = 0;
     }
   };
   for (size_t p = 0; p < n; ++p) each_tap(p, [&](size_t q) { inv_off[q + 1]++; });
   for (size_t q = 0; q < (size_t)R * B; ++q) inv_off[q + 1] += inv_off[q];
-  std::vector<int32_t> inv_idx((size_t)inv_off.back() + 1);
-  {
-    std::vector<int32_t> cur(inv_off.begin(), inv_off.end() - 1);
-    for (size_t p = 0; p < n; ++p) each_tap(p, [&](size_t q) { inv_idx[cur[q]++] = (int32_t)p; });
-  }
+  inv_idx.assign((size_t)inv_off.back() + 1, 0);
+  std::vector<int32_t> cur(inv_off.begin(), inv_off.end() - 1);
+  for (size_t p = 0; p < n; ++p) each_tap(p, [&](size_t q) { inv_idx[cur[q]++] = (int32_t)p; });
+}
+
+}  // namespace sfe
+
+using namespace sfe;
+
+extern "C" {
+
+int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_host, int rows, int cols, int R, int B,
+                    double width, double height, sfe_maps **out) {
+  SFE_REQUIRE(ctx && out, "sfe_maps_create: null context or out pointer");
+  *out = nullptr;
+  SFE_REQUIRE(map_x_host && map_y_host, "sfe_maps_create: null map pointer");
+  SFE_REQUIRE(rows > 0 && cols > 0 && R > 0 && B > 0, "sfe_maps_create: non-positive shape");
+  SFE_REQUIRE((long long)rows * cols < (1ll << 31), "sfe_maps_create: Cartesian image too large");
+  SFE_CUDA(cudaSetDevice(ctx->device));
+  std::vector<MapEntry> tab;
+  std::vector<int32_t> inv_off, inv_idx;
+  build_map_table(map_x_host, map_y_host, rows, cols, R, B, tab);
+  build_inverse_lists(tab, R, B, inv_off, inv_idx);
+  const size_t n = tab.size();
   sfe_maps *m = new sfe_maps();
   m->rows = rows, m->cols = cols, m->R = R, m->B = B, m->width = width, m->height = height, m->device = ctx->device;
   m->table = nullptr, m->inv_off = nullptr, m->inv_idx = nullptr;
@@ -484,6 +515,25 @@ void sfe_maps_destroy(sfe_maps *m) {
   if (m->inv_off) cudaFree(m->inv_off);
   if (m->inv_idx) cudaFree(m->inv_idx);
   delete m;
+}
+
+int sfe_maps_inverse_lists_host(const float *map_x_host, const float *map_y_host, int rows, int cols, int R, int B,
+                                int32_t *off_out, int32_t *idx_out, int64_t idx_capacity, int64_t *n_entries) {
+  SFE_REQUIRE(map_x_host && map_y_host && off_out && n_entries, "sfe_maps_inverse_lists_host: null pointer");
+  SFE_REQUIRE(rows > 0 && cols > 0 && R > 0 && B > 0 && (long long)rows * cols < (1ll << 31),
+              "sfe_maps_inverse_lists_host: bad shape");
+  std::vector<MapEntry> tab;
+  std::vector<int32_t> inv_off, inv_idx;
+  build_map_table(map_x_host, map_y_host, rows, cols, R, B, tab);
+  build_inverse_lists(tab, R, B, inv_off, inv_idx);
+  *n_entries = inv_off.back();
+  memcpy(off_out, inv_off.data(), inv_off.size() * sizeof(int32_t));
+  if (*n_entries > idx_capacity || (idx_out == nullptr && *n_entries > 0)) {
+    set_error("sfe_maps_inverse_lists_host: %lld entries do not fit the index buffer", (long long)*n_entries);
+    return SFE_ERR_CAPACITY;
+  }
+  memcpy(idx_out, inv_idx.data(), (size_t)*n_entries * sizeof(int32_t));
+  return SFE_OK;
 }
 
 int sfe_cart_points_dev(sfe_ctx *ctx, const sfe_maps *maps, const uint8_t *mask_dev, const uint32_t *bits_dev,
