@@ -17,8 +17,17 @@ iterations, window of 3 previous frames).  One step = one batch through sfe_fron
           code) on a bounded sample of the same frames, one thread
   --impl reference   the reference arm: that CPU path on all host cores (rank 0 only under torchrun)
 
-Multi-GPU: one process per GPU (torchrun), frames sharded by rank (weak scaling: F frames per GPU per
-step), no collective on the data path; NCCL only for the barrier / max-over-ranks of the timing.
+  config3_icp   BASELINE config 3 (2 000 x 20 000-point scan matches, 20 iterations and the shipped checkers) on
+          rank 0: pairs/s over 8 waves of 148 problems, ms per wave
+  config5   BASELINE config 5: a FIXED backlog of 80 000 such pairs held by rank 0, sharded over the N ranks
+          (strong scaling): pair batches leave rank 0 by grouped NCCL send/recv (sonar_slam_b200/dist.py), are
+          solved while the next batch arrives, and the 48-byte results come back by NCCL gather; pairs/s with and
+          without the scatter in the timed region
+
+Multi-GPU: one process per GPU (torchrun).  The headline `value` shards frames by rank (weak scaling: F frames
+per GPU per step) with no collective on the data path; config5 is the path with a real exchange (scatter of pair
+batches from rank 0, gather of SE(2) results).  NCCL's own log is not suppressed: when NCCL_DEBUG is set and
+NCCL_DEBUG_FILE is not, it is sent to stderr so that stdout stays the one JSON line.
 """
 import argparse
 import json
@@ -47,23 +56,32 @@ def parse():
     ap.add_argument("--frames", type=int, default=4096, help="frames per step and per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=256, help="frames per host->device copy chunk (e2e)")
-    ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--pairs", type=int, default=80000, help="config 5: size of the scan-match backlog (0: skip)")
+    ap.add_argument("--pair-steps", type=int, default=2, help="config 5: timed steps (after one warm-up step)")
+    ap.add_argument("--pair-chunks", type=int, default=8, help="config 5: pieces per shard in the pipelined scatter")
     return ap.parse_args()
 
 
+NCU_SUMMARY = os.path.join("profiles", "r02_ncu_full_summaries.json")
+NCU_KEY = "prof_cfar_u8gate4"
+
+
 def ncu_traffic_per_frame():
-    """dram read+write bytes per frame of the pipeline's CFAR kernel, from the committed ncu --set full
-    capture (profiles/r01_ncu_full_summaries.json, 4096-frame launch); None if absent."""
+    """(dram read+write bytes per frame, source) of the pipeline's CFAR kernel.  ncu cannot run inside a timed
+    bench (it replays kernels), so this is STATIC: read from this round's committed `ncu --set full` capture of the
+    same kernel on a 4096-frame launch (tools/prof_cfar.py 4096 u8 bits); (None, reason) if that file is absent."""
     try:
-        with open(os.path.join(REPO, "profiles", "r01_ncu_full_summaries.json")) as f:
-            d = json.load(f)["prof_cfar_u8lut"]
+        with open(os.path.join(REPO, NCU_SUMMARY)) as f:
+            d = json.load(f)[NCU_KEY]
 
         def gb(v):
             x, unit = v.split()
             return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
-        return (gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])) / 4096.0
-    except Exception:  # noqa: BLE001
-        return None
+        return (gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])) / 4096.0, \
+            f"static: {NCU_SUMMARY}[{NCU_KEY}] (ncu --set full of the same kernel, 4096-frame launch)"
+    except Exception as e:  # noqa: BLE001
+        return None, f"no committed ncu capture ({type(e).__name__})"
 
 
 def measured_peak():
@@ -125,13 +143,18 @@ _W = {}
 
 def _cpu_init(bearings):
     from oracle import oracle as orc
+    try:  # one thread per worker process: the pool is the parallelism
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:  # noqa: BLE001
+        pass
     _W["geo"] = _cpu_geometry(bearings)
     _W["prm"] = orc.IcpParams(smooth_length=0, max_iterations=20)
 
 
 def _cpu_cloud(img):
     from oracle import pipeline_ref
-    return pipeline_ref.frame_cloud(img, _W["geo"], tau=TAU_SOCA, use_reference=True)
+    return pipeline_ref.slam_cloud(pipeline_ref.frame_cloud(img, _W["geo"], tau=TAU_SOCA, use_reference=True))
 
 
 def _cpu_match(job):
@@ -161,46 +184,81 @@ def cpu_pipeline(frames, poses, bearings, pool=None):
     return time.perf_counter() - t0
 
 
+def host_cores():
+    """(cores this process may run on, cores the machine reports).  A `fork` pool sized by os.cpu_count() ignores
+    cgroup / affinity limits and oversubscribes a restricted box (the round-1 reference arm swung 3.6x between two
+    runs for that reason); the affinity mask is what the scheduler will actually give us."""
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = os.cpu_count() or 1
+    return usable, os.cpu_count() or usable
+
+
 def run_reference(args):
-    """--impl reference: the CPU path on all host cores, bounded sample per step."""
+    """--impl reference: the CPU path on all usable host cores, bounded sample per step, median of the steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     import torch  # noqa: F401  (frame renderer)
     from sonar_slam_b200 import synth
-    cores = os.cpu_count() or 1
+    cores, reported = host_cores()
     n = max(16, min(8 * cores, 1024))
     d = synth.make_trajectory_frames(n, seed=0)
     frames, poses = d["frames"].numpy(), d["poses_odom"]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(d["bearings"],)) as pool:
-        for _ in range(args.warmup):
-            cpu_pipeline(frames[:max(16, cores)], poses, d["bearings"], pool)
+        for _ in range(max(1, args.warmup)):   # warm-up on the FULL sample: page-in, pool start-up, CPU clocks
+            cpu_pipeline(frames, poses, d["bearings"], pool)
         secs = [cpu_pipeline(frames, poses, d["bearings"], pool) for _ in range(args.steps)]
-    t = float(np.mean(secs))
+    t = float(np.median(secs))
     from oracle import oracle as orc
     val = n / t
     line = {"metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "config4-pipeline: bounded sample of the bag replay per step",
-                       "frames_per_step": n, "image": [R, B], "icp_iterations": 20, "window": 3},
-            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores,
+                       "frames_per_step": n, "image": [R, B], "icp_iterations": 20, "window": 3,
+                       "timing": "median of the timed steps; every step is the full sample",
+                       "step_seconds": [round(x, 4) for x in secs]},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "cores_reported_by_os": reported,
                              "kind": "reference+port" if orc.have_reference() else "port",
-                             "sample": f"{n} frames/step, frame-parallel over {cores} processes: CFAR = reference "
-                                       "cfar.cpp compiled unmodified (oracle/_ref) when present, cv2.remap, restated "
-                                       "libpointmatcher/PCL filters + ICP (oracle/)"},
+                             "sample": f"{n} frames/step, frame-parallel over {cores} processes (= len(os.sched_"
+                                       f"getaffinity(0)); os.cpu_count() = {reported}): CFAR = reference cfar.cpp "
+                                       "compiled unmodified (oracle/_ref) when present, cv2.remap, restated "
+                                       "libpointmatcher/PCL filters + ICP (oracle/), keyframe clouds as SLAM reads "
+                                       "them (lateral sign flip, slam_ros.py:169-170)"},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------ GPU side
+def make_pair_backlog(P, device, n_scenes=32, ns=2000, nt=20000):
+    """Config 3 / 5 input on `device`: P (source, target, guess) records tiled from `n_scenes` seeded scenes of
+    synth.make_icp_pair (2 000-point scan vs 20 000-point submap, identity guess).  The solver
+    keeps no state between problems, so repeating scenes does not help it; the bytes moved are those of P distinct
+    pairs.  Scenes whose thinned target falls short of `nt` points are skipped (records have a fixed size)."""
+    import torch
+    from sonar_slam_b200 import synth
+    src, tgt, seed = [], [], 0
+    while len(src) < n_scenes:
+        a, b, _ = synth.make_icp_pair(seed, n_source=ns, n_target=nt)
+        seed += 1
+        if len(a) == ns and len(b) == nt:
+            src.append(a), tgt.append(b)
+    src_s = torch.from_numpy(np.stack(src)).to(device)
+    tgt_s = torch.from_numpy(np.stack(tgt)).to(device)
+    idx = torch.arange(P, device=device) % n_scenes
+    return src_s[idx].contiguous(), tgt_s[idx].contiguous(), torch.eye(3, device=device).repeat(P, 1, 1).contiguous()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from sonar_slam_b200 import _lib, ops, pipeline, synth
+    from sonar_slam_b200 import dist as sdist
     from sonar_slam_b200.bruce_slam.feature_extraction import FeatureExtraction
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,8 +268,15 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- this benchmark has no CPU fallback for the product path")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL's log is left alone (the driver counts ranks in it); it only moves off stdout, which carries the JSON line
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        opts = None
+        try:  # high-priority communication stream: send/recv kernels are scheduled as soon as an SM frees up
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:  # noqa: BLE001
+            opts = None
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     F, K, W = args.frames, args.steps, args.warmup
 
     # ---- synthetic bag replay for this rank (frames stay resident in HBM; > L2 by far: F*256 KiB)
@@ -240,13 +305,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident leg
+    # ---- device-resident leg (no stage events inside the timed loop)
     for _ in range(W):
         fe.run_dev(frames_dev.data_ptr(), poses, F)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
-    fe.set_timing(True)
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -256,8 +320,6 @@ def run_ours(args):
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launches - l0
-    stage = fe.get_timing()
-    fe.set_timing(False)
 
     # ---- end-to-end leg: host buffers in, results out, through one C-ABI call per step
     for _ in range(W):
@@ -268,6 +330,13 @@ def run_ours(args):
         fe.run_host(host_frames, poses, chunk_frames=args.chunk, out=out)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    # ---- separate pass with per-stage CUDA events on the launch stream (the roofline's kernel time, stage shares)
+    fe.set_timing(True)
+    for _ in range(K):
+        fe.run_dev(frames_dev.data_ptr(), poses, F)
+    stage = fe.get_timing()
+    fe.set_timing(False)
     clk = clocks.stop()
     barrier()
 
@@ -276,18 +345,91 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
 
+    # ---- config 3 (rank 0) and config 5 (all ranks): 2 000 x 20 000-point scan matches
+    cfg3, cfg5 = None, None
+    prm20 = _lib.IcpParams(smooth_length=0, max_iterations=20)
+    try:
+        if rank == 0:
+            P3 = 8 * ctx.sm_count
+            s3, t3, g3 = make_pair_backlog(P3, f"cuda:{local}", n_scenes=16)
+            cfg3 = {"pairs": P3, "source_points": 2000, "target_points": 20000, "waves": 8}
+            for name, prm in (("fixed20", prm20), ("checkers", _lib.IcpParams())):
+                for _ in range(2):
+                    r3 = sdist.unpack_results(sdist._default_icp(s3, t3, g3, prm))
+                ts = []
+                for _ in range(3):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    r3 = sdist.unpack_results(sdist._default_icp(s3, t3, g3, prm))
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b))
+                ms = float(np.median(ts))
+                cfg3[name] = {"pairs_per_s": P3 / (ms * 1e-3), "ms_per_wave_of_148": ms / 8, "ms": ms,
+                              "mean_iterations": float(r3["iterations"].float().mean().item()),
+                              "converged": int((r3["status"] == 0).sum().item())}
+            del s3, t3, g3
+        if args.pairs > 0:
+            P5 = args.pairs
+            sa, ta, ga = make_pair_backlog(P5, f"cuda:{local}") if rank == 0 else (None, None, None)
+            barrier()
+
+            def timed(fn, reps):
+                """max over ranks of the device time of `fn` (CUDA events on this rank's stream), per repetition"""
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    res = fn()
+                b.record()
+                barrier()
+                return max_over_ranks(a.elapsed_time(b)) / reps, res
+
+            # (a) the whole step: pipelined scatter -> solve -> gather (the product path, sonar_slam_b200/dist.py)
+            step = lambda: sdist.run_pair_backlog(P5, 2000, 20000, prm20, sa, ta, ga, chunks=args.pair_chunks)
+            timed(step, 1)
+            ms_step, packed = timed(step, args.pair_steps)
+            # (b) its parts, each alone: one-shot scatter; solve + gather on the resident shard
+            ms_scatter, shard = timed(lambda: sdist.scatter_pairs(P5, 2000, 20000, sa, ta, ga), 1)
+            solve = lambda: sdist.gather_pair_results(sdist._default_icp(*shard, prm20), P5)
+            timed(solve, 1)
+            ms_solve, packed2 = timed(solve, args.pair_steps)
+            if rank == 0:
+                r5 = sdist.unpack_results(packed)
+                same = bool(torch.equal(packed, packed2))
+                per_pair = (2000 + 20000) * 8 + 36
+                cfg5 = {"pairs_total": P5, "scaling": "strong (fixed backlog)", "n_gpus": world,
+                        "pairs_per_s_incl_scatter_gather": P5 / (ms_step * 1e-3),
+                        "pairs_per_s_without_scatter": P5 / (ms_solve * 1e-3),
+                        "ms_step_pipelined": ms_step, "ms_solve_and_gather_resident": ms_solve,
+                        "ms_scatter_alone": ms_scatter,
+                        "scatter_GBps_from_rank0": (P5 - P5 // world) * per_pair / (ms_scatter * 1e-3) / 1e9 if world > 1 else None,
+                        "scatter_bytes": (P5 - P5 // world) * per_pair if world > 1 else 0,
+                        "gather_bytes": P5 * 4 * sdist.RESULT_WORDS if world > 1 else 0,
+                        "chunks_per_shard": args.pair_chunks, "timed_steps": args.pair_steps,
+                        "converged": int((r5["status"] == 0).sum().item()),
+                        "pipelined_equals_resident_results": same,
+                        "transport": "grouped NCCL send/recv (dist.batch_isend_irecv) + NCCL gather" if world > 1 else "none (one rank)"}
+            del sa, ta, ga, shard
+    except Exception as e:  # noqa: BLE001
+        cfg5 = {"error": f"{type(e).__name__}: {e}"}
+        if world > 1:
+            raise
+
     if rank == 0:
         peak, peak_src = measured_peak()
         total_ms = sum(v[0] for v in stage.values())
         cfar_ms, cfar_calls = stage["cfar"]
         cfar_bytes = F * R * B * (1 + 1 / 8)            # uint8 image in, bit plane out, per launch
         achieved = cfar_bytes / (cfar_ms / max(1, cfar_calls) * 1e-3) / 1e9
+        traffic_pf, traffic_src = ncu_traffic_per_frame()
         line = {
             "metric": METRIC, "value": world * F * K / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config4-pipeline: synthetic bag replay, CFAR(SOCA 40/10, Pfa 0.1, gate 65) -> "
-                                   "cloud -> voxel 0.5 m -> outlier(1.0 m, 5) -> ICP 20 iterations vs 3-frame submap",
+                                   "cloud -> voxel 0.5 m -> outlier(1.0 m, 5) -> keyframe cloud (x, -z) -> ICP 20 "
+                                   "iterations vs 3-frame submap",
                        "frames_per_step_per_gpu": F, "image": [R, B], "image_dtype": "u8", "icp_iterations": 20,
                        "window": 3, "sharding": "frames by rank, no data-path collective",
                        "l2": f"inputs larger than L2 ({F * R * B / 2**20:.0f} MiB of frames per step)",
@@ -297,13 +439,16 @@ def run_ours(args):
             "e2e": {"value": world * F * K / e2e_s, "unit": "frames/s",
                     "h2d_bytes_per_step": F * R * B + F * 4 * 9 * 4, "d2h_bytes_per_step": F * (36 + 16)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "cfar_u8_lut_kernel<SOCA, bits>", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "cfar_u8_gate4_kernel<SOCA, bits>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (ncu_traffic_per_frame() * F) if ncu_traffic_per_frame() else None,
+                         "traffic": (traffic_pf * F) if traffic_pf else None, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": cfar_bytes,
-                         "kernel_ms_per_launch": cfar_ms / max(1, cfar_calls)},
+                         "kernel_ms_per_launch": cfar_ms / max(1, cfar_calls),
+                         "timing": "CUDA events on the launch stream around the kernel, separate pass after the "
+                                   "timed steps (the timed `value` loop carries no stage events)"},
             "stage_share": {k: (v[0] / total_ms if total_ms else None) for k, v in stage.items()},
             "stage_ms_per_step": {k: v[0] / K for k, v in stage.items()},
+            "config3_icp": cfg3, "config5": cfg5,
         }
         # config 2 (SURVEY 8(d) primary definition: float32 frames in, uint8 mask out), same run
         try:
@@ -337,11 +482,13 @@ def run_ours(args):
                 _cpu_init(d["bearings"])
                 sample = frames_dev[:n].cpu().numpy()
                 secs = cpu_pipeline(sample, poses[:n], d["bearings"])
+                usable, reported = host_cores()
                 line["cpu_baseline"] = {"value": n / secs, "unit": "frames/s", "cores": 1,
                                         "kind": "reference+port" if orc.have_reference() else "port",
-                                        "sample": f"first {n} frames of the step, one thread ({os.cpu_count()} host cores "
-                                                  "present): reference cfar.cpp (unmodified, oracle/_ref) + cv2.remap + "
-                                                  "restated libpointmatcher/PCL filters and ICP (oracle/)"}
+                                        "sample": f"first {n} frames of the step ({secs:.1f} s), one thread ({usable} "
+                                                  f"usable host cores, os.cpu_count() = {reported}): reference cfar.cpp "
+                                                  "(unmodified, oracle/_ref) + cv2.remap + restated libpointmatcher/PCL "
+                                                  "filters and ICP (oracle/)"}
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(line), flush=True)

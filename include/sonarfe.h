@@ -177,7 +177,12 @@ typedef struct {
   float min_diff_rot;     /* DifferentialTransformationChecker          icp.yaml:26  0.01 */
   float min_diff_trans;   /*                                            icp.yaml:27   0.1 */
   int smooth_length;      /* (0: differential checker off; <= 15)        icp.yaml:28     4 */
-  int flags;              /* bit 0: MaxDist filter compares squared distance with maxDist itself */
+  int flags;              /* bit 0: MaxDist filter compares squared distance with maxDist itself
+                             bit 1: parity mode -- every sum over points (reference mean, pair means, cross-
+                                    covariance) is a SEQUENTIAL float32 sum in point order, the accumulation order of
+                                    the CPU oracle (oracle/icp_ref.c); results are then bit-identical to it.  Default
+                                    (bit clear): float32 terms accumulated in float64, order-independent and ~1e-4
+                                    closer to exact arithmetic; a few per cent faster. */
 } sfe_icp_params;
 SFE_API void sfe_icp_params_default(sfe_icp_params *p);
 
@@ -235,6 +240,13 @@ typedef struct {
   int cap_points;           /* capacity (rows) reserved per frame for its Cartesian cloud; a frame with more
                                detections is truncated and reported as SFE_ICP_TOO_LARGE */
   int cap_source, cap_target; /* largest source / target cloud the scan matcher accepts */
+  int flip_lateral;         /* != 0 (default 1, the reference's behaviour): the cloud SLAM matches on is
+                               (forward, -lateral).  FeatureExtraction publishes points as xyz = [p0, 0, p1]
+                               (feature_extraction.py:182) and the SLAM node reads them back as
+                               np.c_[x, -z] = (p0, -p1) (slam_ros.py:169-170), so every keyframe cloud -- scan-match
+                               source, window submap, and the clouds sfe_frontend_results_dev exposes -- has its
+                               lateral coordinate negated AFTER the feature filters.  0 keeps
+                               FeatureExtraction.callback's own (p0, p1) convention. */
 } sfe_frontend_params;
 SFE_API void sfe_frontend_params_default(sfe_frontend_params *p);
 

@@ -51,6 +51,22 @@ def transform_points(points, pose):
     return points.dot(T[:2, :2].T) + T[:2, 2]
 
 
+def transform_points_explicit(points, pose):
+    """The same transform with the float32 rounding spelled out, independent of which BLAS kernel numpy's float32
+    `dot` dispatches to on the host: x' = fl32(fma(y, r01, fl32(x * r00))) + tx (and likewise y') -- what numpy's
+    float32 [N,2] @ [2,2] gives on FMA hardware and what the device kernel evaluates (sonarfe.h, sfe_costmap_*).
+    The fused multiply-add is formed in float64 (the product of two float32 values is exact there)."""
+    T = pose.matrix().astype(np.float32)
+    p = np.asarray(points, np.float32)
+    x, y = p[:, 0], p[:, 1]
+
+    def row(r0, r1, t):
+        first = (x * r0).astype(np.float32)
+        acc = (y.astype(np.float64) * np.float64(r1) + first.astype(np.float64)).astype(np.float32)
+        return (acc + t).astype(np.float32)
+    return np.stack([row(T[0, 0], T[0, 1], T[0, 2]), row(T[1, 0], T[1, 1], T[1, 2])], 1)
+
+
 def target_grid(target_points, point_noise):
     """slam.py:506-530 -> (grid uint8 [rows, cols] 0/255, xmin, ymin, resolution, dilate_hs)."""
     import cv2
@@ -71,9 +87,10 @@ def target_grid(target_points, point_noise):
     return cv2.dilate(grid, kernel), xmin, ymin, resolution, dilate_hs
 
 
-def cost_of_transform(grid, xmin, ymin, resolution, source_points, sample_transform):
-    """slam.py:553-567 for one sample_transform (a Pose2)."""
-    points = transform_points(source_points, sample_transform)
+def cost_of_transform(grid, xmin, ymin, resolution, source_points, sample_transform, explicit=False):
+    """slam.py:553-567 for one sample_transform (a Pose2).  explicit=True: the float32 dot product with its
+    rounding spelled out (transform_points_explicit) instead of numpy's BLAS-dependent `dot`."""
+    points = (transform_points_explicit if explicit else transform_points)(source_points, sample_transform)
     r = np.int32(np.round((points[:, 1] - ymin) / resolution))
     c = np.int32(np.round((points[:, 0] - xmin) / resolution))
     inside = (0 <= r) & (r < grid.shape[0]) & (0 <= c) & (c < grid.shape[1])

@@ -127,7 +127,7 @@ FrontendParams._fields_ = [
     ("R", c_int), ("B", c_int), ("cfar_alg", c_int), ("train_hs", c_int), ("guard_hs", c_int), ("rank", c_int),
     ("tau", c_double), ("gate_enable", c_int), ("gate_threshold", c_double), ("resolution", c_float),
     ("outlier_radius", c_double), ("outlier_min_points", c_int), ("window", c_int), ("submap_resolution", c_float),
-    ("min_points", c_int), ("icp", IcpParams), ("cap_points", c_int), ("cap_source", c_int), ("cap_target", c_int)]
+    ("min_points", c_int), ("icp", IcpParams), ("cap_points", c_int), ("cap_source", c_int), ("cap_target", c_int), ("flip_lateral", c_int)]
 
 
 def check(rc, what=""):

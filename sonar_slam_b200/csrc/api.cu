@@ -21,6 +21,7 @@ int ensure(sfe_ctx *ctx, Buffer &b, size_t bytes) {
   if (bytes <= b.cap) return SFE_OK;
   // grow-only; the old block may still be in use by enqueued work -> stream-ordered free
   if (b.ptr) SFE_CUDA(cudaFreeAsync(b.ptr, ctx->stream));
+  if (b.ptr == ctx->cfar_lut_buf) ctx->cfar_lut_buf = nullptr;  // the cached table went with the block
   b.ptr = nullptr, b.cap = 0;
   size_t want = bytes + bytes / 4 + 256;
   SFE_CUDA(cudaMallocAsync(&b.ptr, want, ctx->stream));

@@ -160,7 +160,7 @@ struct CfarStep {  // per-thread streaming state (all in registers; indices are 
   float xr[CF_RING];  // x[rn - a]      at slot (J - a) & 31
   float wr[CF_RING];  // W[rn - a] = sum of the 20 cells ending at rn - a
   float w;            // W[rn - 1]
-  float bad;          // > 0 once a non-integer cell was seen
+  bool bad;           // set once a cell was seen that is not an integer of magnitude < 2^22 (fraction, NaN, +-inf)
   float mx;           // max |cell|
 };
 
@@ -174,8 +174,9 @@ __device__ __forceinline__ void cfar_step(CfarStep &s, const float xn, uint8_t (
   constexpr int I = J % CF_CH;
   if (sizeof(InT) == 4) {
     // integer-valued?  (x + 1.5*2^23) - 1.5*2^23 == x  <=>  x integer and |x| < 2^22
+    // (`!=` is true for unordered operands: a NaN cell, or inf - inf, flags the strip; fmaxf would drop the NaN)
     const float rt = (xn + 12582912.0f) - 12582912.0f;
-    s.bad = fmaxf(s.bad, fabsf(rt - xn));
+    s.bad = s.bad || (rt - xn != 0.f);
     s.mx = fmaxf(s.mx, fabsf(xn));
   }
   // cell under test r, newest cell rn = r + 25:
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(CF_W, 4)
   CfarStep s;
 #pragma unroll
   for (int i = 0; i < CF_RING; ++i) s.xr[i] = 0.f, s.wr[i] = 0.f;
-  s.w = 0.f, s.bad = 0.f, s.mx = 0.f;
+  s.w = 0.f, s.bad = false, s.mx = 0.f;
   const float c_hi = p.c_hi, c_lo = p.c_lo;
   const float gate = p.gate_on ? p.gate_f : -INFINITY;
 
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(CF_W, 4)
       }
     }
   }
-  if (sizeof(InT) == 4 && (s.bad > 0.f || !(s.mx <= 262144.0f))) p.flags[blockIdx.x] = 1;
+  if (sizeof(InT) == 4 && (s.bad || !(s.mx <= 262144.0f))) p.flags[blockIdx.x] = 1;
   if (MASK && tid == 0) tma_wait_all<0>();
 }
 
@@ -484,6 +485,216 @@ __global__ void __launch_bounds__(CF_W, 5)
     }
   }
   if (MASK && tid == 0) tma_wait_all<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// uint8 streaming kernel for the node's configuration (CFAR + amplitude gate fused, feature_extraction.py:223-224):
+// FOUR beams per thread, SIMD inside 32-bit registers.  With the gate on, a cell can only be a detection when
+// x >= g_min = min_S M[S] (M = the pass table of cfar_u8_lut_kernel; g_min is the gate for the shipped parameters),
+// which is rare in sonar imagery (Rayleigh speckle: ~0.2 % of the cells).  So the per-cell work is only what keeps
+// the window sums current, and the table look-up / compare / bit set runs in a rarely taken branch:
+//   * one LDS.32 brings the new cells of 4 adjacent beams (bytes); the raw words also form the cell ring;
+//   * window sums (<= 20*255 < 2^16) live as 16-bit lanes, two beams per register: PRMT spreads the bytes of the
+//     entering and the leaving cell to 16-bit lanes, one IADD3 per beam pair updates the sums (lanes cannot carry
+//     into each other: every lane stays in [0, 5100]); a 32-deep register delay line yields the leading sum;
+//   * "does any of the 4 cells under test reach g_min" is two integer instructions on the packed bytes
+//     (((x + k) | x) & 0x80808080, k = (128 - g_min) * 0x01010101); only then VIMNMX.U16x2 forms min/max(lead, lag)
+//     and the table M[S] is consulted per beam, setting bits (atomicOr) / bytes in a zero-initialised shared tile.
+// ~2.5 instructions per cell instead of ~9 (cuobjdump -sass: profiles/), all-integer, exact: identical to the
+// table kernel by construction (the branch is a necessary condition; the decision is the same table compare).
+// A strip is 512 beams (128 threads x 4); 16-row chunks arrive by TMA as two [16 x 256] boxes per stage.  Block b
+// consumes chunk b (newest cell rn = 16 b + i) and decides cell r = rn - 25, so every block touches ONE tile.
+constexpr int CG_BEAMS = 4;
+constexpr int CG_W = CF_W * CG_BEAMS;  // beams per strip
+constexpr int CG_NS = 4;               // input ring depth
+constexpr int CG_GMIN_LO = 16;         // below this the "rare branch" is not rare: use the table kernel
+
+struct CfarStepG {
+  uint32_t xr[CF_RING];                // cells, 4 beams per word
+  uint32_t wl[CF_RING], wh[CF_RING];   // window sums W[rn - a]: beams 0,1 / beams 2,3 as 16-bit lanes
+  uint32_t w_lo, w_hi;                 // W[rn - 1]
+};
+
+// shared-memory layout of cfar_u8_gate4_kernel (dynamic): tile [CG_NS][2][16][256] | obits [2][16][16] |
+// full_bar [CG_NS] | lut [lut_n padded to 8] | omask [2][16][512] (MASK only)
+constexpr size_t CG_OFF_OBITS = (size_t)CG_NS * CF_CH * CG_W;
+constexpr size_t CG_OFF_BAR = CG_OFF_OBITS + sizeof(uint32_t) * 2 * CF_CH * (CG_W / 32);
+constexpr size_t CG_OFF_LUT = CG_OFF_BAR + 64;
+__host__ __device__ __forceinline__ size_t cg_off_omask(int lut_n) {
+  return CG_OFF_LUT + ((sizeof(uint16_t) * (size_t)((lut_n + 7) / 8 * 8) + 15) & ~size_t(15));
+}
+extern __shared__ __align__(128) unsigned char cg_smem[];
+
+// The rare branch: decide the four cells of one row.  `row` = ob * 16 + i indexes the output tiles.
+template <int ALG, bool MASK, bool BITS>
+__device__ __noinline__ void cfar_gate_hit(const uint32_t xc4, const uint32_t lead_lo, const uint32_t lead_hi,
+                                           const uint32_t lag_lo, const uint32_t lag_hi, const int row,
+                                           const int lut_n, const int tid, const int nvalid) {
+  const uint16_t *lut = reinterpret_cast<const uint16_t *>(cg_smem + CG_OFF_LUT);
+  uint32_t s_lo, s_hi;
+  if (ALG == SFE_CFAR_CA) s_lo = lead_lo + lag_lo, s_hi = lead_hi + lag_hi;  // <= 10200 per lane
+  else if (ALG == SFE_CFAR_SOCA) s_lo = __vminu2(lead_lo, lag_lo), s_hi = __vminu2(lead_hi, lag_hi);
+  else s_lo = __vmaxu2(lead_lo, lag_lo), s_hi = __vmaxu2(lead_hi, lag_hi);
+  uint32_t set = 0;
+#pragma unroll
+  for (int k = 0; k < CG_BEAMS; ++k) {
+    const int x = (int)((xc4 >> (8 * k)) & 255u);
+    const int S = (int)(((k < 2 ? s_lo : s_hi) >> (16 * (k & 1))) & 0xffffu);
+    if (k < nvalid && x >= (int)lut[S]) set |= 1u << k;
+  }
+  if (set == 0) return;
+  if (BITS)
+    atomicOr(reinterpret_cast<uint32_t *>(cg_smem + CG_OFF_OBITS) + row * (CG_W / 32) + (tid >> 3),
+             set << ((tid & 7) * CG_BEAMS));
+  if (MASK)  // bytes 0/1 of the four beams: spread the 4 bits to 4 bytes
+    *reinterpret_cast<uint32_t *>(cg_smem + cg_off_omask(lut_n) + (size_t)row * CG_W + CG_BEAMS * tid) =
+        (set & 1u) | ((set & 2u) << 7) | ((set & 4u) << 14) | ((set & 8u) << 21);
+}
+
+template <int ALG, bool MASK, bool BITS, bool EDGE, int J>
+__device__ __forceinline__ void cfar_step_g(CfarStepG &s, const uint32_t xn4, const uint32_t gate_add,
+                                            const int lut_n, const int ob, const int R, const int r, const int tid,
+                                            const int nvalid) {
+  constexpr int I = J % CF_CH;
+  const uint32_t x20 = s.xr[(J + CF_RING - CF_T) % CF_RING];
+  const uint32_t xc4 = s.xr[(J + CF_RING - CF_HALF) % CF_RING];
+  const uint32_t lead_lo = s.wl[(J + CF_RING - (CF_HALF + CF_G + 1)) % CF_RING];
+  const uint32_t lead_hi = s.wh[(J + CF_RING - (CF_HALF + CF_G + 1)) % CF_RING];
+  const uint32_t lag_lo = s.w_lo + __byte_perm(xn4, 0u, 0x4140u) - __byte_perm(x20, 0u, 0x4140u);
+  const uint32_t lag_hi = s.w_hi + __byte_perm(xn4, 0u, 0x4342u) - __byte_perm(x20, 0u, 0x4342u);
+  s.w_lo = lag_lo, s.w_hi = lag_hi;
+  s.wl[J % CF_RING] = lag_lo, s.wh[J % CF_RING] = lag_hi;
+  s.xr[J % CF_RING] = xn4;
+  // any of the four cells under test >= g_min?  (a carry out of a byte only happens when that byte already
+  // qualifies, so the any-test is exact; which bytes qualify is settled in cfar_gate_hit)
+  if (((xc4 + gate_add) | xc4) & 0x80808080u) {
+    if (!EDGE || (r >= CF_HALF && r < R - CF_HALF))
+      cfar_gate_hit<ALG, MASK, BITS>(xc4, lead_lo, lead_hi, lag_lo, lag_hi, ob * CF_CH + I, lut_n, tid, nvalid);
+  }
+}
+
+template <int ALG, bool MASK, bool BITS, bool EDGE, int Q>
+__device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][CF_CH][CG_W / 2],
+                                               uint32_t (*obits)[CF_CH][CG_W / 32], uint8_t (*omask)[CF_CH][CG_W],
+                                               uint64_t *full_bar, const CUtensorMap *in_map,
+                                               const int lut_n, const CfarParams &p, const int blk,
+                                               const int nchunks, const int tid, const int f, const int col0,
+                                               const uint32_t gate_add, const int nvalid) {
+  const int r0 = blk * CF_CH - CF_HALF;  // first output row of this block
+  constexpr int ob = Q & 1;
+  const int st = blk & (CG_NS - 1);
+  const bool has = EDGE ? (blk < nchunks) : true;
+  uint32_t xin[CF_CH];
+  if (has) {
+    mbar_wait(&full_bar[st], (blk / CG_NS) & 1);
+    const uint32_t *trow = reinterpret_cast<const uint32_t *>(&tile[st][tid >> 6][0][(tid & 63) * CG_BEAMS]);
+#pragma unroll
+    for (int i = 0; i < CF_CH; ++i) xin[i] = trow[i * (CG_W / 2 / 4)];
+  } else {
+#pragma unroll
+    for (int i = 0; i < CF_CH; ++i) xin[i] = 0u;  // below the image: zero cells (never decide anything)
+  }
+#define SFE_STEP(I) \
+  cfar_step_g<ALG, MASK, BITS, EDGE, Q * CF_CH + I>(s, xin[I], gate_add, lut_n, ob, p.R, r0 + I, tid, nvalid);
+  SFE_STEP(0) SFE_STEP(1) SFE_STEP(2) SFE_STEP(3) SFE_STEP(4) SFE_STEP(5) SFE_STEP(6) SFE_STEP(7)
+  SFE_STEP(8) SFE_STEP(9) SFE_STEP(10) SFE_STEP(11) SFE_STEP(12) SFE_STEP(13) SFE_STEP(14) SFE_STEP(15)
+#undef SFE_STEP
+  __syncthreads();  // every thread has read tile[st]; the block's detections are in obits[ob] / omask[ob]
+  if (tid == 0 && blk + CG_NS < nchunks) {
+    mbar_arrive_expect_tx(&full_bar[st], CF_CH * CG_W);
+    tma_load_3d(&tile[st][0][0][0], in_map, &full_bar[st], col0, (blk + CG_NS) * CF_CH, f);
+    tma_load_3d(&tile[st][1][0][0], in_map, &full_bar[st], col0 + CG_W / 2, (blk + CG_NS) * CF_CH, f);
+  }
+  if (EDGE && r0 + CF_CH <= 0) return;  // nothing to write yet (and nothing was set)
+  // hand the 16 rows to global memory and clear them for the block after next (the thread that reads a word is
+  // the one that clears it; the buffer is next written after the NEXT block's barrier)
+  if (BITS) {
+    const int i = tid >> 3, wq = (tid & 7) * 2;  // 16 rows x 16 words = 128 x uint2
+    uint2 *src = reinterpret_cast<uint2 *>(&obits[ob][i][wq]);
+    const uint2 v = *src;
+    *src = make_uint2(0u, 0u);
+    const int r = r0 + i, w = (col0 >> 5) + wq;
+    if (r >= 0 && r < p.R) {
+      uint32_t *dst = p.bits + ((size_t)f * p.R + r) * p.words_per_row + w;
+      if (w + 1 < p.words_per_row && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0) {
+        *reinterpret_cast<uint2 *>(dst) = v;
+      } else {
+        if (w < p.words_per_row) dst[0] = v.x;
+        if (w + 1 < p.words_per_row) dst[1] = v.y;
+      }
+    }
+  }
+  if (MASK) {
+#pragma unroll
+    for (int j = 0; j < CF_CH * (CG_W / 16) / CF_W; ++j) {  // 16 rows x 32 uint4 over 128 threads
+      const int idx = tid + j * CF_W, i = idx / (CG_W / 16), sg = idx % (CG_W / 16);
+      uint4 *src = reinterpret_cast<uint4 *>(&omask[ob][i][sg * 16]);
+      const uint4 v = *src;
+      *src = make_uint4(0u, 0u, 0u, 0u);
+      const int r = r0 + i, c = col0 + sg * 16;
+      if (r >= 0 && r < p.R && c < p.B)  // B % 16 == 0 and mask 16-byte aligned (checked by the host)
+        *reinterpret_cast<uint4 *>(p.mask + ((size_t)f * p.R + r) * p.B + c) = v;
+    }
+  }
+}
+
+template <int ALG, bool MASK, bool BITS>
+__global__ void __launch_bounds__(CF_W, MASK ? 3 : 4)
+    cfar_u8_gate4_kernel(const __grid_constant__ CUtensorMap in_map, CfarParams p, const uint16_t *__restrict__ lut_g,
+                         const int lut_n, const uint32_t gate_add) {
+  uint8_t(*tile)[2][CF_CH][CG_W / 2] = reinterpret_cast<uint8_t(*)[2][CF_CH][CG_W / 2]>(cg_smem);
+  uint32_t(*obits)[CF_CH][CG_W / 32] = reinterpret_cast<uint32_t(*)[CF_CH][CG_W / 32]>(cg_smem + CG_OFF_OBITS);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(cg_smem + CG_OFF_BAR);
+  uint16_t *lut = reinterpret_cast<uint16_t *>(cg_smem + CG_OFF_LUT);
+  uint8_t(*omask)[CF_CH][CG_W] = reinterpret_cast<uint8_t(*)[CF_CH][CG_W]>(cg_smem + cg_off_omask(lut_n));
+
+  const int tid = threadIdx.x;
+  const int f = blockIdx.x / p.strips;
+  const int col0 = (blockIdx.x % p.strips) * CG_W;
+  const int R = p.R;
+  const int nchunks = (R + CF_CH - 1) / CF_CH;
+  if (tid == 0) {
+    prefetch_tmap(&in_map);
+    for (int st = 0; st < CG_NS; ++st) mbar_init(&full_bar[st], 1);
+    fence_mbar_init();
+    for (int c = 0; c < CG_NS && c < nchunks; ++c) {
+      mbar_arrive_expect_tx(&full_bar[c], CF_CH * CG_W);
+      tma_load_3d(&tile[c][0][0][0], &in_map, &full_bar[c], col0, c * CF_CH, f);
+      tma_load_3d(&tile[c][1][0][0], &in_map, &full_bar[c], col0 + CG_W / 2, c * CF_CH, f);
+    }
+  }
+  for (int i = tid; i * 8 < lut_n; i += CF_W) reinterpret_cast<uint4 *>(lut)[i] = reinterpret_cast<const uint4 *>(lut_g)[i];
+  if (BITS)
+    for (int i = tid; i < 2 * CF_CH * (CG_W / 32); i += CF_W) (&obits[0][0][0])[i] = 0u;
+  if (MASK)
+    for (int i = tid; i < 2 * CF_CH * CG_W / 16; i += CF_W) reinterpret_cast<uint4 *>(&omask[0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  CfarStepG s;
+#pragma unroll
+  for (int i = 0; i < CF_RING; ++i) s.xr[i] = 0u, s.wl[i] = 0u, s.wh[i] = 0u;
+  s.w_lo = 0u, s.w_hi = 0u;
+  const int nvalid = min(max(p.B - (col0 + CG_BEAMS * tid), 0), CG_BEAMS);
+  // block b: newest cells rn = 16 b .. 16 b + 15, decides rows rn - 25; the last decided row is R - 1
+  const int nblk = (R + CF_HALF + CF_CH - 1) / CF_CH;
+  for (int b2 = 0; b2 * 2 < nblk; ++b2) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int blk = b2 * 2 + q;
+      if (blk < nblk) {
+        const int r0 = blk * CF_CH - CF_HALF;
+        const bool interior = (r0 >= CF_HALF) && (r0 + CF_CH - 1 < R - CF_HALF) && blk < nchunks;
+#define SFE_BLOCK(EDGE_, Q_) \
+  cfar_block16_g<ALG, MASK, BITS, EDGE_, Q_>(s, tile, obits, omask, full_bar, &in_map, lut_n, p, blk, nchunks, tid, f, col0, gate_add, nvalid)
+        if (interior) {
+          if (q == 0) SFE_BLOCK(false, 0); else SFE_BLOCK(false, 1);
+        } else {
+          if (q == 0) SFE_BLOCK(true, 0); else SFE_BLOCK(true, 1);
+        }
+#undef SFE_BLOCK
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -660,6 +871,27 @@ static int launch_u8_lut(sfe_ctx *ctx, const CUtensorMap &in_map, const CUtensor
   return SFE_OK;
 }
 
+template <int ALG>
+static int launch_u8_gate4(sfe_ctx *ctx, const CUtensorMap &in_map, const CfarParams &p, const uint16_t *lut, int lut_n,
+                           uint32_t gate_add) {
+  const bool m = p.mask != nullptr, b = p.bits != nullptr;
+  const int grid = p.F * p.strips;
+  const size_t smem = cg_off_omask(lut_n) + (m ? 2 * CF_CH * CG_W : 0);
+#define SFE_GO(M_, B_)                                                                                              \
+  do {                                                                                                              \
+    SFE_CUDA(cudaFuncSetAttribute(cfar_u8_gate4_kernel<ALG, M_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                  (int)smem));                                                                      \
+    cfar_u8_gate4_kernel<ALG, M_, B_><<<grid, CF_W, smem, ctx->stream>>>(in_map, p, lut, lut_n, gate_add);          \
+  } while (0)
+  if (m && b) SFE_GO(true, true);
+  else if (m) SFE_GO(true, false);
+  else SFE_GO(false, true);
+#undef SFE_GO
+  SFE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SFE_OK;
+}
+
 template <typename InT>
 static int launch_exact(sfe_ctx *ctx, const InT *img, const CfarParams &p, const uint8_t *only_flagged) {
   size_t smem = 0;
@@ -737,25 +969,42 @@ int cfar_run(sfe_ctx *ctx, const void *img, int dtype, int F, int R, int B, int 
       return launch_exact<float>(ctx, (const float *)img, p, p.flags);  // re-does flagged strips only
     }
     if (thr == nullptr && isfinite(tau)) {
-      // integer kernel with the threshold table (re-uploaded only when the parameters change)
-      static thread_local std::vector<uint16_t> lut_host;
-      static thread_local double key[5] = {-1, 0, 0, 0, 0};
-      static thread_local const void *key_buf = nullptr;
+      // integer kernels with the threshold table (re-uploaded only when the parameters change; the cache key lives
+      // in the context next to the buffer it describes)
+      std::vector<uint16_t> lut_host;
       build_u8_lut(p, lut_host);
       const int lut_n = (int)lut_host.size();
-      lut_host.resize((lut_host.size() + 7) / 8 * 8, 256);  // pad for the kernel's 16-byte copies
+      int g_min = 256;
+      for (uint16_t v : lut_host) g_min = v < g_min ? v : g_min;
+      lut_host.resize((lut_host.size() + 7) / 8 * 8, 256);  // pad for the kernels' 16-byte copies
       rc = ensure(ctx, ctx->scratch[SCR_CFAR_LUT], 65536);  // [0, 32 KiB): this table, [32 KiB, 64 KiB): the OS table
       if (rc != SFE_OK) return rc;
-      const double k5[5] = {(double)alg, tau, (double)p.gate_on, p.gate_d, (double)lut_host.size()};
-      if (memcmp(k5, key, sizeof(key)) != 0 || key_buf != ctx->scratch[SCR_CFAR_LUT].ptr) {
+      const double k6[6] = {(double)alg, tau, (double)p.gate_on, p.gate_d, (double)lut_host.size(), 1.0};
+      if (memcmp(k6, ctx->cfar_lut_key, sizeof(k6)) != 0 || ctx->cfar_lut_buf != ctx->scratch[SCR_CFAR_LUT].ptr) {
         SFE_CUDA(cudaMemcpyAsync(ctx->scratch[SCR_CFAR_LUT].ptr, lut_host.data(), lut_host.size() * sizeof(uint16_t),
                                  cudaMemcpyHostToDevice, ctx->stream));
-        SFE_CUDA(cudaStreamSynchronize(ctx->stream));  // lut_host is reused by the next call
-        memcpy(key, k5, sizeof(key));
-        key_buf = ctx->scratch[SCR_CFAR_LUT].ptr;
+        SFE_CUDA(cudaStreamSynchronize(ctx->stream));  // lut_host is a local
+        memcpy(ctx->cfar_lut_key, k6, sizeof(k6));
+        ctx->cfar_lut_buf = ctx->scratch[SCR_CFAR_LUT].ptr;
       }
       const uint16_t *lut = (const uint16_t *)ctx->scratch[SCR_CFAR_LUT].ptr;
       const int n = lut_n;
+      const char *force = getenv("SFE_CFAR_U8_KERNEL");  // development switch: "lut" / "gate4"
+      const bool want_gate4 = force ? (strcmp(force, "gate4") == 0) : true;
+      if (want_gate4 && g_min >= (force ? 1 : CG_GMIN_LO) && g_min <= 128 && (mask != nullptr || bits != nullptr)) {
+        // gated 4-beams-per-thread kernel: its own tensor map (two [16 x 256] boxes per chunk)
+        CUtensorMap in4;
+        rc = encode_tensor_map_3d(&in4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, img, B, R, F, CG_W / 2, CF_CH, 1);
+        if (rc != SFE_OK) return rc;
+        CfarParams q = p;
+        q.strips = (B + CG_W - 1) / CG_W;
+        const uint32_t gate_add = 0x01010101u * (uint32_t)(128 - g_min);
+        switch (alg) {
+          case SFE_CFAR_CA: return launch_u8_gate4<SFE_CFAR_CA>(ctx, in4, q, lut, n, gate_add);
+          case SFE_CFAR_SOCA: return launch_u8_gate4<SFE_CFAR_SOCA>(ctx, in4, q, lut, n, gate_add);
+          default: return launch_u8_gate4<SFE_CFAR_GOCA>(ctx, in4, q, lut, n, gate_add);
+        }
+      }
       switch (alg) {
         case SFE_CFAR_CA: return launch_u8_lut<SFE_CFAR_CA>(ctx, in_map, out_map, p, lut, n);
         case SFE_CFAR_SOCA: return launch_u8_lut<SFE_CFAR_SOCA>(ctx, in_map, out_map, p, lut, n);

@@ -52,6 +52,13 @@ struct sfe_ctx {
   void *pinned = nullptr;   // small pinned host block for async result reads
   size_t pinned_cap = 0;
   uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
+  // per-context caches (they describe buffers / attributes owned by THIS context, so they live here and not in
+  // thread-local statics: a new context may get a recycled device address, two contexts may share a thread)
+  double cfar_lut_key[6] = {-1, 0, 0, 0, 0, 0};  // parameters of the table held in scratch[SCR_CFAR_LUT]
+  const void *cfar_lut_buf = nullptr;            // ... and the buffer it was uploaded to (null = none)
+  size_t icp_attr_smem[4] = {0, 0, 0, 0};        // cudaFuncAttributeMaxDynamicSharedMemorySize set per ICP instantiation
+  struct OccEntry { size_t smem; int threads, per_sm, variant; } icp_occ[8] = {};
+  int icp_occ_next = 0;
 };
 
 struct sfe_maps {  // per-geometry polar->Cartesian sampling table (featx.cu)

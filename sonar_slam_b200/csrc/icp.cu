@@ -52,8 +52,17 @@ struct IcpBatch {
   int P, ns_max, nt_max, max_cells;
   float cell_scale;  // grid cell = cell_scale * sqrt(area / n)
   sfe_icp_params prm;
-  uint16_t *orig_ws;  // [gridDim.x][nt_max]
+  uint16_t *orig_ws;  // [slots][nt_max]
+  float4 *seq_ws;     // [slots][ns_max] per-point terms of the sequential sums (flags bit 1 only)
+  int slot_by_smid;   // workspace slot = %smid (one CTA per SM, one CTA per problem) instead of blockIdx.x
 };
+
+constexpr int ICP_SM_SLOTS = 256;  // >= %nsmid on every sm_100 part
+__device__ __forceinline__ unsigned icp_smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
 
 __device__ __forceinline__ void mat3_mul_rn(const float *a, const float *b, float *c) {
   float r[9];
@@ -147,6 +156,7 @@ struct IcpShared {  // small fixed-size part of the shared state
   float wred[4 * 16];      // per-warp partials of the bounding-box / maximum reductions
   float hq_w[ICP_HIST], hq_z[ICP_HIST], ht_x[ICP_HIST], ht_y[ICP_HIST];
   int hn;
+  float seq[4];               // results of the sequential sums (flags bit 1)
   int cnx, cny;               // coarse occupancy grid (ICP_COARSE x ICP_COARSE fine cells per coarse cell)
   uint32_t coarse[ICP_COARSE_WORDS];
 };
@@ -200,7 +210,26 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
   return __uint_as_float(prefix);
 }
 
-__global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
+// exact sequential float32 sum of n values p[0], p[stride], ... in index order (flags bit 1: the accumulation
+// order of oracle/icp_ref.c).  The loads of eight terms are issued together; the adds stay in order.
+__device__ __forceinline__ float seq_sum_f32(const float *p, int n, int stride) {
+  float s = 0.f;
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[(size_t)(i + k) * stride];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, v[k]);
+  }
+  for (; i < n; ++i) s = __fadd_rn(s, p[(size_t)i * stride]);
+  return s;
+}
+
+// One instantiation per CTA size so that the register budget follows the launch shape (a single
+// __launch_bounds__(512) build capped the 128-thread class at 64 registers and spilled).
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [IcpShared][sorted float2 nt_max][cells u32][reading float2 ns_max][dist f32 ns_max][match u16 ns_max]
   //         [prev u16 ns_max][qstate u8 ns_max]
@@ -224,11 +253,21 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   int red_phase = 0, tot_phase = 0, sel_pass = 0;  // rotation counters of the one-barrier reductions (CTA-uniform)
   for (int h = threadIdx.x; h < 3 * 256; h += blockDim.x) (&sh.hist[0][0])[h] = 0;
-  uint16_t *orig = b.orig_ws + (size_t)blockIdx.x * b.nt_max;
+  // Problems that allow one CTA per SM (config 3: ~200 KB of shared memory) are launched one CTA per problem, not
+  // as persistent CTAs: problems of unequal length (checker mode: 4-40 iterations) balance themselves, and SMs
+  // free up every few milliseconds so that concurrent NCCL send/recv kernels (the config-5 scatter) get scheduled.
+  // The per-CTA global workspace is then indexed by the SM the CTA runs on.
+  const unsigned slot = b.slot_by_smid ? icp_smid() : blockIdx.x;
+  if (b.slot_by_smid && slot >= ICP_SM_SLOTS) __trap();
+  uint16_t *orig = b.orig_ws + (size_t)slot * b.nt_max;
   const sfe_icp_params prm = b.prm;
   const float max_d2 = __fmul_rn(prm.matcher_max_dist, prm.matcher_max_dist);
   const float out_d2 = (prm.flags & 1) ? prm.outlier_max_dist : __fmul_rn(prm.outlier_max_dist, prm.outlier_max_dist);
   const int smooth = min(prm.smooth_length, ICP_HIST - 1);
+  // flags bit 1: every sum over points is a sequential float32 sum in point order, as in oracle/icp_ref.c (the
+  // parity mode: results are bit-identical to the oracle); default: float32 terms accumulated in float64.
+  const bool seq = (prm.flags & 2) != 0;
+  float4 *seq_ws = seq ? b.seq_ws + (size_t)slot * b.ns_max : nullptr;
 
   for (int p = blockIdx.x; p < b.P; p += gridDim.x) {
     const int si = b.src_id ? b.src_id[p] : p, ti = b.tgt_id ? b.tgt_id[p] : p;
@@ -261,10 +300,17 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
 
     // ---- 1. mean of the reference, bounding box of the centred reference
     {
-      double s[2] = {0.0, 0.0}, tot[2];
-      for (int i = tid; i < nt; i += nthr) s[0] += (double)tgt[2 * i], s[1] += (double)tgt[2 * i + 1];
-      block_sum<2>(s, sh.red, red_phase, tot);
-      const float mx = (float)(tot[0] / (double)nt), my = (float)(tot[1] / (double)nt);
+      float mx, my;
+      if (seq) {
+        if (tid < 2) sh.seq[tid] = __fdiv_rn(seq_sum_f32(tgt + tid, nt, 2), (float)nt);
+        __syncthreads();
+        mx = sh.seq[0], my = sh.seq[1];
+      } else {
+        double s[2] = {0.0, 0.0}, tot[2];
+        for (int i = tid; i < nt; i += nthr) s[0] += (double)tgt[2 * i], s[1] += (double)tgt[2 * i + 1];
+        block_sum<2>(s, sh.red, red_phase, tot);
+        mx = (float)(tot[0] / (double)nt), my = (float)(tot[1] / (double)nt);
+      }
       float mn_x = INFINITY, mn_y = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
       for (int i = tid; i < nt; i += nthr) {
         const float x = tgt[2 * i] - mx, y = tgt[2 * i + 1] - my;
@@ -501,42 +547,89 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpBatch b) {
       }
 
       // 3c. kept pairs: count and sums for the means
-      double s5[5] = {0, 0, 0, 0, 0}, t5[5];
-      for (int i = tid; i < ns; i += nthr) {
-        bool keep = match[i] != 0xffff;
-        if (prm.outlier_max_dist > 0.f) keep = keep && (dist[i] <= out_d2);
-        if (prm.trim_ratio >= 0.f) keep = keep && (dist[i] <= limit);
-        if (!keep) {
-          match[i] = 0xffff;
-          continue;
+      int n_keep;
+      float mrx, mry, mfx, mfy;
+      if (seq) {
+        int cnt = 0;
+        for (int i = tid; i < ns; i += nthr) {
+          bool keep = match[i] != 0xffff;
+          if (prm.outlier_max_dist > 0.f) keep = keep && (dist[i] <= out_d2);
+          if (prm.trim_ratio >= 0.f) keep = keep && (dist[i] <= limit);
+          if (!keep) {
+            match[i] = 0xffff;
+            seq_ws[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // x + (+0) == x: dropped pairs do not disturb the sums
+            continue;
+          }
+          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+          const float2 r = sorted[match[i]];
+          seq_ws[i] = make_float4(q.x, q.y, r.x, r.y);
+          ++cnt;
         }
-        const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-        const float2 r = sorted[match[i]];
-        s5[0] += 1.0, s5[1] += (double)q.x, s5[2] += (double)q.y, s5[3] += (double)r.x, s5[4] += (double)r.y;
+        n_keep = block_total(cnt, &sh.tot[0][0], tot_phase);  // (its barrier publishes seq_ws to the CTA)
+      } else {
+        double s5[5] = {0, 0, 0, 0, 0}, t5[5];
+        for (int i = tid; i < ns; i += nthr) {
+          bool keep = match[i] != 0xffff;
+          if (prm.outlier_max_dist > 0.f) keep = keep && (dist[i] <= out_d2);
+          if (prm.trim_ratio >= 0.f) keep = keep && (dist[i] <= limit);
+          if (!keep) {
+            match[i] = 0xffff;
+            continue;
+          }
+          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+          const float2 r = sorted[match[i]];
+          s5[0] += 1.0, s5[1] += (double)q.x, s5[2] += (double)q.y, s5[3] += (double)r.x, s5[4] += (double)r.y;
+        }
+        block_sum<5>(s5, sh.red, red_phase, t5);
+        n_keep = (int)t5[0];
+        mrx = (float)t5[1], mry = (float)t5[2], mfx = (float)t5[3], mfy = (float)t5[4];
       }
-      block_sum<5>(s5, sh.red, red_phase, t5);
-      const int n_keep = (int)t5[0];
       if (n_keep == 0) {
         if (tid == 0) sh.status = ICP_NO_POINT;
         __syncthreads();
         break;
       }
+      if (seq) {
+        if (tid < 4) sh.seq[tid] = seq_sum_f32(reinterpret_cast<const float *>(seq_ws) + tid, ns, 4);
+        __syncthreads();
+        mrx = sh.seq[0], mry = sh.seq[1], mfx = sh.seq[2], mfy = sh.seq[3];
+        __syncthreads();  // sh.seq and seq_ws are rewritten below
+      }
       const float winv = __fdiv_rn(1.0f, (float)n_keep);
-      const float mrx = __fmul_rn((float)t5[1], winv), mry = __fmul_rn((float)t5[2], winv);
-      const float mfx = __fmul_rn((float)t5[3], winv), mfy = __fmul_rn((float)t5[4], winv);
+      mrx = __fmul_rn(mrx, winv), mry = __fmul_rn(mry, winv);
+      mfx = __fmul_rn(mfx, winv), mfy = __fmul_rn(mfy, winv);
 
       // 3d. cross-covariance of the centred pairs
-      double s4[4] = {0, 0, 0, 0}, t4[4];
-      for (int i = tid; i < ns; i += nthr) {
-        if (match[i] == 0xffff) continue;
-        const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-        const float2 r = sorted[match[i]];
-        const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
-        const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
-        s4[0] += (double)__fmul_rn(qx, px), s4[1] += (double)__fmul_rn(qx, py);
-        s4[2] += (double)__fmul_rn(qy, px), s4[3] += (double)__fmul_rn(qy, py);
+      double t4[4];
+      if (seq) {
+        for (int i = tid; i < ns; i += nthr) {
+          if (match[i] == 0xffff) {
+            seq_ws[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+          }
+          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+          const float2 r = sorted[match[i]];
+          const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
+          const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
+          seq_ws[i] = make_float4(__fmul_rn(qx, px), __fmul_rn(qx, py), __fmul_rn(qy, px), __fmul_rn(qy, py));
+        }
+        __syncthreads();
+        if (tid < 4) sh.seq[tid] = seq_sum_f32(reinterpret_cast<const float *>(seq_ws) + tid, ns, 4);
+        __syncthreads();
+        t4[0] = (double)sh.seq[0], t4[1] = (double)sh.seq[1], t4[2] = (double)sh.seq[2], t4[3] = (double)sh.seq[3];
+      } else {
+        double s4[4] = {0, 0, 0, 0};
+        for (int i = tid; i < ns; i += nthr) {
+          if (match[i] == 0xffff) continue;
+          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+          const float2 r = sorted[match[i]];
+          const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
+          const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
+          s4[0] += (double)__fmul_rn(qx, px), s4[1] += (double)__fmul_rn(qx, py);
+          s4[2] += (double)__fmul_rn(qy, px), s4[3] += (double)__fmul_rn(qy, py);
+        }
+        block_sum<4>(s4, sh.red, red_phase, t4);
       }
-      block_sum<4>(s4, sh.red, red_phase, t4);
 
       // 3e. rigid fit, T_iter update, checkers (one thread)
       if (tid == 0) {
@@ -736,33 +829,43 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   // CTA size follows the source size (one NN query per thread and iteration is the sweet spot)
   // (measured on the config-4 replay: 256 threads beat 128 and 512 for ~360-point sources)
   const int threads = force_threads > 0 ? force_threads : (b.ns_max <= 640 ? 128 : (b.ns_max <= 1536 ? 256 : ICP_THREADS));
-  // the attribute / occupancy queries are cached per (smem, threads): the front end calls this per copy chunk
-  struct OccEntry { size_t smem; int threads, per_sm, dev; };
-  static thread_local OccEntry occ[4] = {};
-  static thread_local size_t attr_smem = 0;
-  static thread_local int attr_dev = -1, occ_next = 0;
-  if (attr_dev != ctx->device || smem > attr_smem) {
-    SFE_CUDA(cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem, attr_dev = ctx->device;
+  SFE_REQUIRE(threads == 128 || threads == 256 || threads == 512, "icp: CTA size must be 128, 256 or 512 (got %d)", threads);
+  // instantiation: (threads, register budget).  512-thread CTAs whose shared memory allows only one per SM get the
+  // full 128 registers.
+  const int variant = threads == 128 ? 0 : (threads == 256 ? 1 : (smem > 110 * 1024 ? 3 : 2));
+  const void *fn = variant == 0   ? (const void *)icp_kernel<128, 6>
+                   : variant == 1 ? (const void *)icp_kernel<256, 4>
+                   : variant == 2 ? (const void *)icp_kernel<512, 2>
+                                  : (const void *)icp_kernel<512, 1>;
+  // the attribute / occupancy queries are cached in the context per (variant, smem): the front end calls this per
+  // copy chunk
+  if (smem > ctx->icp_attr_smem[variant]) {
+    SFE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->icp_attr_smem[variant] = smem;
   }
   int c_per_sm = 0;
-  for (const OccEntry &e : occ)
-    if (e.per_sm > 0 && e.smem == smem && e.threads == threads && e.dev == ctx->device) c_per_sm = e.per_sm;
+  for (const auto &e : ctx->icp_occ)
+    if (e.per_sm > 0 && e.smem == smem && e.threads == threads && e.variant == variant) c_per_sm = e.per_sm;
   if (c_per_sm == 0) {
     int q = 1;
-    SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, icp_kernel, threads, smem));
+    SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, threads, smem));
     c_per_sm = q < 1 ? 1 : q;
-    occ[occ_next] = OccEntry{smem, threads, c_per_sm, ctx->device};
-    occ_next = (occ_next + 1) % 4;
+    ctx->icp_occ[ctx->icp_occ_next] = {smem, threads, c_per_sm, variant};
+    ctx->icp_occ_next = (ctx->icp_occ_next + 1) % 8;
   }
   const int per_sm = c_per_sm;
   int grid = ctx->sm_count * per_sm;
   if (grid > P) grid = P;
-  int rc = ensure(ctx, ctx->scratch[SCR_ICP], (size_t)grid * b.nt_max * sizeof(uint16_t));
+  int slots = grid;
+  if (per_sm == 1 && P > grid) b.slot_by_smid = 1, slots = ICP_SM_SLOTS, grid = P;  // one CTA per problem
+  const size_t orig_bytes = ((size_t)slots * b.nt_max * sizeof(uint16_t) + 15) & ~size_t(15);
+  const size_t seq_bytes = (prm->flags & 2) ? (size_t)slots * b.ns_max * sizeof(float4) : 0;
+  int rc = ensure(ctx, ctx->scratch[SCR_ICP], orig_bytes + seq_bytes);
   if (rc != SFE_OK) return rc;
   b.orig_ws = (uint16_t *)ctx->scratch[SCR_ICP].ptr;
-  icp_kernel<<<grid, threads, smem, ctx->stream>>>(b);
-  SFE_CUDA(cudaGetLastError());
+  b.seq_ws = seq_bytes ? (float4 *)((char *)ctx->scratch[SCR_ICP].ptr + orig_bytes) : nullptr;
+  void *args[] = {(void *)&b};
+  SFE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, ctx->stream));
   ctx->launches++;
   return SFE_OK;
 }

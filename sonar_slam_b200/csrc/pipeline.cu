@@ -41,15 +41,28 @@ constexpr int FE_ICP_SMALL_SRC = 640, FE_ICP_SMALL_TGT = 1536, FE_ICP_SMALL_THRE
 
 // T_ab = pose_a^-1 * pose_b as float32 3x3 (gtsam Pose2::between, then matrix().astype(float32)).
 // Evaluated on the host in double (libm), so the float32 matrices the kernels see are the ones a
-// Python caller would compute.
+// Python caller would compute.  Rotation as gtsam forms it: Rot2 holds (cos, sin) and between() multiplies
+// r_a^-1 * r_b, i.e. c = ca*cb + sa*sb, s = ca*sb - sa*cb (not cos/sin of the angle difference; the two differ by
+// ~1e-16, which matters only on a float32 rounding boundary); translation = r_a.unrotate(t_b - t_a).
 static void pose_between(const double *a, const double *b, float *T) {
-  const double ca = cos(a[2]), sa = sin(a[2]);
+  const double ca = cos(a[2]), sa = sin(a[2]), cb = cos(b[2]), sb = sin(b[2]);
   const double dx = b[0] - a[0], dy = b[1] - a[1];
-  const double x = ca * dx + sa * dy, y = -sa * dx + ca * dy, th = b[2] - a[2];
-  const double c = cos(th), s = sin(th);
+  const double x = ca * dx + sa * dy, y = -sa * dx + ca * dy;
+  const double c = ca * cb + sa * sb, s = ca * sb - sa * cb;
   T[0] = (float)c, T[1] = (float)-s, T[2] = (float)x;
   T[3] = (float)s, T[4] = (float)c, T[5] = (float)y;
   T[6] = 0.f, T[7] = 0.f, T[8] = 1.f;
+}
+
+// A6: the keyframe cloud as SLAM holds it.  The feature node publishes xyz = [p0, 0, p1]
+// (feature_extraction.py:182); SLAM reads np.c_[x, -z] = (p0, -p1) (slam_ros.py:169-170).  Negation is exact, so
+// flipping the float32 cloud after the filters equals what the reference's float32 message round trip gives.
+__global__ void flip_lateral_kernel(float *__restrict__ xy, const int32_t *__restrict__ cnt, int cap, int n) {
+  const int f = blockIdx.x;
+  if (f >= n) return;
+  const int k = min(cnt[f], cap);
+  float *p = xy + 2 * (size_t)f * cap;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) p[2 * i + 1] = -p[2 * i + 1];
 }
 
 // offsets helper: off[i] = i * stride
@@ -81,8 +94,10 @@ __global__ void __launch_bounds__(256)
     const float *src = clouds + 2 * (size_t)k * cap;
     for (int j = threadIdx.x; j < n && base + j < tgt_cap; j += blockDim.x) {
       const float x = src[2 * j], y = src[2 * j + 1];
-      out[2 * (base + j)] = __fadd_rn(__fadd_rn(__fmul_rn(x, t0), __fmul_rn(y, t1)), t2);
-      out[2 * (base + j) + 1] = __fadd_rn(__fadd_rn(__fmul_rn(x, t3), __fmul_rn(y, t4)), t5);
+      // numpy's float32 `points.dot(R.T) + t` (slam_objects.py:196): fma(y, r01, x * r00) + tx -- the same
+      // convention as the costmap kernels (globalinit.cu), pinned against numpy in tests/test_oracle_globalinit.py
+      out[2 * (base + j)] = __fadd_rn(__fmaf_rn(y, t1, __fmul_rn(x, t0)), t2);
+      out[2 * (base + j) + 1] = __fadd_rn(__fmaf_rn(y, t4, __fmul_rn(x, t3)), t5);
     }
     base = min(base + n, tgt_cap);
   }
@@ -158,6 +173,7 @@ void sfe_frontend_params_default(sfe_frontend_params *p) {
   sfe_icp_params_default(&p->icp);
   p->cap_points = 8192;
   p->cap_source = 1024, p->cap_target = 3072;
+  p->flip_lateral = 1;
 }
 
 #define FE_ALLOC(ptr, bytes)                                                        \
@@ -285,6 +301,8 @@ static int fe_upload_poses(sfe_frontend *fe, const double *poses, int n) {
   return SFE_OK;
 }
 
+static const float *fe_cloud(const sfe_frontend *fe, const int32_t **cnt);
+
 // stages 1-3 on frames [f0, f0+n): CFAR (bit plane) -> Cartesian points -> downsample -> outlier removal.
 // Final per-frame clouds end in xy_a / cnt_c (or wherever the last enabled filter wrote; see cloud()).
 static int fe_features(sfe_frontend *fe, const uint8_t *frames_dev, int f0, int n) {
@@ -320,6 +338,15 @@ static int fe_features(sfe_frontend *fe, const uint8_t *frames_dev, int f0, int 
                             p.outlier_min_points, dst, fe->idx, fe->cnt_c + f0);
     fe_toc(fe);
     if (rc != SFE_OK) return rc;
+  }
+  if (p.flip_lateral) {
+    const int32_t *cnt;
+    float *cloud = const_cast<float *>(fe_cloud(fe, &cnt));
+    fe_tic(fe, SFE_FE_OUTLIER);
+    flip_lateral_kernel<<<n, 128, 0, ctx->stream>>>(cloud + 2 * (size_t)f0 * cap, cnt + f0, (int)cap, n);
+    fe_toc(fe);
+    SFE_CUDA(cudaGetLastError());
+    ctx->launches++;
   }
   return SFE_OK;
 }
@@ -367,10 +394,14 @@ static int fe_match(sfe_frontend *fe, int f0, int n) {
   // untouched; the second, sized for the capacities, only takes those.
   const int ns_small = p.cap_source < FE_ICP_SMALL_SRC ? p.cap_source : FE_ICP_SMALL_SRC;
   const int nt_small = p.cap_target < FE_ICP_SMALL_TGT ? p.cap_target : FE_ICP_SMALL_TGT;
+  // class_mode 1 leaves oversize problems untouched for the second launch; when the capacities are not larger than
+  // the small class there is no second launch and this one must report them itself (SFE_ICP_TOO_LARGE)
+  const bool two = ns_small < p.cap_source || nt_small < p.cap_target;
   int rc = icp_run(ctx, &p.icp, cloud, fe->off_pts + f0, cnt + f0, tgt, fe->off_tgt + f0, tcnt + f0, p.min_points,
                    nullptr, nullptr, n, ns_small, nt_small, fe->guess + 9 * (size_t)f0, fe->T + 9 * (size_t)f0,
-                   fe->iters + f0, fe->inliers + f0, fe->status + f0, fe->cnt_a + f0, cap, 1, 0, 0, FE_ICP_SMALL_THREADS);
-  if (rc == SFE_OK && (ns_small < p.cap_source || nt_small < p.cap_target))
+                   fe->iters + f0, fe->inliers + f0, fe->status + f0, fe->cnt_a + f0, cap, two ? 1 : 0, 0, 0,
+                   FE_ICP_SMALL_THREADS);
+  if (rc == SFE_OK && two)
     rc = icp_run(ctx, &p.icp, cloud, fe->off_pts + f0, cnt + f0, tgt, fe->off_tgt + f0, tcnt + f0, p.min_points,
                  nullptr, nullptr, n, p.cap_source, p.cap_target, fe->guess + 9 * (size_t)f0,
                  fe->T + 9 * (size_t)f0, fe->iters + f0, fe->inliers + f0, fe->status + f0, fe->cnt_a + f0, cap, 2,

@@ -72,3 +72,173 @@ def gather_results(local, n_halo, n_total, dst=0):
     out = {k: np.concatenate([g[k] for g in gathered]) for k in own}
     assert all(len(v) == n_total for v in out.values())
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Backlog of independent scan matches (BASELINE config 5): P (source, target, guess) problems held
+# by rank `src` are sharded in contiguous blocks (shard_bounds), streamed to their ranks with grouped NCCL
+# send/recv (dist.batch_isend_irecv = one ncclGroup per chunk), solved with the batched ICP kernel, and the
+# 48-byte results are gathered back with NCCL.  Clouds of one backlog have a common size (ns / nt points: the
+# benchmark's 2 k / 20 k; real clouds are padded by the caller), so a problem is a fixed-size record and no offsets
+# travel.  No collective sits inside the algorithm: the scatter and the gather are the only communication.
+RESULT_WORDS = 12  # T (9 float32) + iterations, inliers, status (int32) = 48 B per problem
+
+
+def chunk_plan(P, world, chunks):
+    """Every rank's shard is cut into the same number of chunks: plan[r] = [(start, end), ...] (global indices);
+    a chunk may be empty.  Shared by sender and receivers so that their send/recv sizes agree."""
+    plan = []
+    for s, e in shard_bounds(P, world):
+        n = e - s
+        per = -(-n // chunks) if n else 0
+        plan.append([(min(s + c * per, e), min(s + (c + 1) * per, e)) for c in range(chunks)])
+    return plan
+
+
+def pack_results(res):
+    """dict(T [n,3,3] f32, iterations, inliers, status i32) -> int32 [n, RESULT_WORDS]."""
+    n = res["T"].shape[0]
+    out = torch.empty((n, RESULT_WORDS), dtype=torch.int32, device=res["T"].device)
+    out[:, :9] = res["T"].reshape(n, 9).contiguous().view(torch.int32)
+    out[:, 9], out[:, 10], out[:, 11] = res["iterations"], res["inliers"], res["status"]
+    return out
+
+
+def unpack_results(packed):
+    return dict(T=packed[:, :9].contiguous().view(torch.float32).reshape(-1, 3, 3), iterations=packed[:, 9],
+                inliers=packed[:, 10], status=packed[:, 11])
+
+
+def _default_icp(src, tgt, guess, prm):
+    """src [n, ns, 2], tgt [n, nt, 2], guess [n,3,3] cuda tensors -> packed results [n, RESULT_WORDS]."""
+    from . import ops
+    n, ns, nt = src.shape[0], src.shape[1], tgt.shape[1]
+    dev = src.device
+    so = torch.arange(n + 1, dtype=torch.int32, device=dev) * ns
+    to = torch.arange(n + 1, dtype=torch.int32, device=dev) * nt
+    return pack_results(ops.icp(src.reshape(-1, 2), so, tgt.reshape(-1, 2), to, guess, ns, nt, prm))
+
+
+def scatter_pairs(P, ns, nt, src_all=None, tgt_all=None, guess_all=None, src=0, device="cuda"):
+    """One grouped send/recv: rank `src` holds src_all [P,ns,2], tgt_all [P,nt,2], guess_all [P,3,3] (float32, on
+    its device); every rank returns its shard (src, tgt, guess) -- views into the originals on rank `src`."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    s, e = shard_bounds(P, world)[rank]
+    if rank == src:
+        ops_ = []
+        for r, (a, b) in enumerate(shard_bounds(P, world)):
+            if r != src and b > a:
+                ops_ += [dist.P2POp(dist.isend, src_all[a:b], r), dist.P2POp(dist.isend, tgt_all[a:b], r),
+                         dist.P2POp(dist.isend, guess_all[a:b], r)]
+        for q in (dist.batch_isend_irecv(ops_) if ops_ else []):
+            q.wait()
+        return src_all[s:e], tgt_all[s:e], guess_all[s:e]
+    n = e - s
+    out = (torch.empty((n, ns, 2), dtype=torch.float32, device=device),
+           torch.empty((n, nt, 2), dtype=torch.float32, device=device),
+           torch.empty((n, 3, 3), dtype=torch.float32, device=device))
+    if n:
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, t, src) for t in out]):
+            q.wait()
+    return out
+
+
+def gather_pair_results(local_packed, P, dst=0):
+    """NCCL gather of the packed results (shards padded to the largest one); rank `dst` gets [P, RESULT_WORDS]."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    bounds = shard_bounds(P, world)
+    if world == 1:
+        return local_packed
+    n_max = max(e - s for s, e in bounds)
+    pad = torch.zeros((n_max, RESULT_WORDS), dtype=torch.int32, device=local_packed.device)
+    pad[:local_packed.shape[0]] = local_packed
+    parts = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, parts, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([parts[r][:e - s] for r, (s, e) in enumerate(bounds)])
+
+
+def run_pair_backlog(P, ns, nt, prm, src_all=None, tgt_all=None, guess_all=None, chunks=8, src=0, icp_fn=None,
+                     device="cuda"):
+    """The whole config-5 step with the scatter hidden behind the solver: every shard is cut into `chunks` pieces;
+    a communication stream receives piece c+1 (double-buffered) while the compute stream solves piece c; rank `src`
+    solves its own shard straight from the backlog.  Returns the packed results [P, RESULT_WORDS] on rank `src`
+    (None elsewhere).  `icp_fn(src, tgt, guess, prm) -> packed` is injectable (CPU tests run this over gloo)."""
+    icp_fn = icp_fn or _default_icp
+    rank, world = dist.get_rank(), dist.get_world_size()
+    plan = chunk_plan(P, world, chunks)
+    s, e = shard_bounds(P, world)[rank]
+    cuda = torch.device(device).type == "cuda"
+    local = torch.empty((e - s, RESULT_WORDS), dtype=torch.int32, device=device)
+    if world == 1:
+        for a, b in plan[0]:
+            if b > a:
+                local[a - s:b - s] = icp_fn(src_all[a:b], tgt_all[a:b], guess_all[a:b], prm)
+        return local
+    compute = torch.cuda.current_stream() if cuda else None
+    comm = torch.cuda.Stream() if cuda else None
+    if cuda:
+        comm.wait_stream(compute)
+
+    def on_comm():
+        return torch.cuda.stream(comm) if cuda else _Null()
+
+    if rank == src:
+        # stream every other rank's pieces out, chunk by chunk (one NCCL group per chunk), while solving our own
+        for c in range(chunks):
+            ops_ = []
+            for r in range(world):
+                a, b = plan[r][c]
+                if r != src and b > a:
+                    ops_ += [dist.P2POp(dist.isend, src_all[a:b], r), dist.P2POp(dist.isend, tgt_all[a:b], r),
+                             dist.P2POp(dist.isend, guess_all[a:b], r)]
+            with on_comm():
+                for q in (dist.batch_isend_irecv(ops_) if ops_ else []):
+                    q.wait()
+            a, b = plan[src][c]
+            if b > a:
+                local[a - s:b - s] = icp_fn(src_all[a:b], tgt_all[a:b], guess_all[a:b], prm)
+    else:
+        per = max(b - a for a, b in plan[rank])
+        bufs = [(torch.empty((per, ns, 2), dtype=torch.float32, device=device),
+                 torch.empty((per, nt, 2), dtype=torch.float32, device=device),
+                 torch.empty((per, 3, 3), dtype=torch.float32, device=device)) for _ in range(2)] if per else []
+        ready = [torch.cuda.Event() for _ in range(chunks)] if cuda else None
+        freed = [torch.cuda.Event() for _ in range(chunks)] if cuda else None
+
+        def post_recv(c):
+            a, b = plan[rank][c]
+            if b <= a:
+                return
+            with on_comm():
+                if cuda and c >= 2:
+                    comm.wait_event(freed[c - 2])          # the solver is done with this buffer
+                for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, t[:b - a], src) for t in bufs[c & 1]]):
+                    q.wait()
+                if cuda:
+                    ready[c].record(comm)
+        post_recv(0)
+        for c in range(chunks):
+            if c + 1 < chunks:
+                post_recv(c + 1)
+            a, b = plan[rank][c]
+            if b <= a:
+                continue
+            if cuda:
+                compute.wait_event(ready[c])
+            sb, tb, gb = bufs[c & 1]
+            local[a - s:b - s] = icp_fn(sb[:b - a], tb[:b - a], gb[:b - a], prm)
+            if cuda:
+                freed[c].record(compute)
+    if cuda:
+        compute.wait_stream(comm)
+    return gather_pair_results(local, P, dst=src)
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

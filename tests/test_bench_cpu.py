@@ -15,7 +15,7 @@ def test_cpu_pipeline_leg_runs_on_a_tiny_sample():
 
 def test_reference_arm_prints_one_json_line(monkeypatch, capsys):
     import bench
-    monkeypatch.setattr(bench.os, "cpu_count", lambda: 2)
+    monkeypatch.setattr(bench, "host_cores", lambda: (2, 8))   # usable (affinity mask), reported by the OS
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"])
     a = bench.parse()
     bench.run_reference(a)
@@ -27,6 +27,14 @@ def test_reference_arm_prints_one_json_line(monkeypatch, capsys):
         assert k in line, k
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["cores"] == 2 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["cores_reported_by_os"] == 8 and len(line["config"]["step_seconds"]) == 1
+
+
+def test_host_cores_follow_the_affinity_mask():
+    import os
+    import bench
+    usable, reported = bench.host_cores()
+    assert 1 <= usable <= reported and usable == len(os.sched_getaffinity(0))
 
 
 def test_bench_refuses_to_run_the_product_path_without_a_gpu():

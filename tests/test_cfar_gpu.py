@@ -165,3 +165,68 @@ def test_large_batch_checksum_properties(gpu_ctx):
     idx = [0, 100, 255]
     want, _ = _oracle_batch("SOCA", imgs[idx].cpu().numpy(), 20, 5, 0, TAU["SOCA"], gate=65)
     assert np.array_equal(a[idx].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("shape", [(3, 512, 512), (2, 512, 528), (2, 100, 256), (1, 77, 1024), (2, 333, 48),
+                                   (1, 51, 16), (2, 512, 1040)])
+@pytest.mark.parametrize("gate", [16, 65, 127])
+def test_u8_gated_four_beam_kernel(gpu_ctx, shape, gate, monkeypatch):
+    """cfar_u8_gate4_kernel (4 beams per thread, detections decided in a rare branch) against the table kernel
+    it replaces and against the oracle: speckle frames (few candidates), bright frames (every row takes the
+    branch), strips that end inside a 512-beam block, images shorter than the window."""
+    rng = np.random.default_rng(shape[1] * 7 + shape[2] + gate)
+    speckle = np.clip(np.rint(rng.rayleigh(18.0, shape)), 0, 255).astype(np.uint8)
+    bright = rng.integers(0, 256, shape).astype(np.uint8)
+    for imgs in (speckle, bright):
+        dev = torch.from_numpy(imgs).cuda()
+        for alg in ("CA", "SOCA", "GOCA"):
+            monkeypatch.setenv("SFE_CFAR_U8_KERNEL", "gate4")
+            a = ops.cfar(dev, alg, 20, 5, TAU[alg], gate=gate, want_mask=True, want_bits=True)
+            b = ops.cfar(dev, alg, 20, 5, TAU[alg], gate=gate, want_mask=False, want_bits=True)
+            c = ops.cfar(dev, alg, 20, 5, TAU[alg], gate=gate, want_mask=True)
+            monkeypatch.setenv("SFE_CFAR_U8_KERNEL", "lut")
+            ref = ops.cfar(dev, alg, 20, 5, TAU[alg], gate=gate, want_mask=True, want_bits=True)
+            want, _ = _oracle_batch(alg, imgs, 20, 5, 0, TAU[alg], gate=gate)
+            assert np.array_equal(ref["mask"].cpu().numpy(), want), (alg, "table kernel")
+            assert np.array_equal(a["mask"].cpu().numpy(), want), (alg, shape, gate)
+            assert np.array_equal(c["mask"].cpu().numpy(), want), (alg, shape, gate)
+            assert torch.equal(a["bits"], ref["bits"]) and torch.equal(b["bits"], ref["bits"]), (alg, shape, gate)
+            assert np.array_equal(_unpack_bits(b["bits"], shape[2]), want)
+
+
+def test_float_images_with_nan_and_inf(gpu_ctx):
+    """A NaN / +-inf cell must hand its strip to the sequential-order kernel: like cfar.cpp, rows whose windows
+    contain the cell detect nothing (comparisons with NaN are false), rows after it detect again."""
+    rng = np.random.default_rng(9)
+    imgs = np.rint(rng.rayleigh(18.0, (3, 512, 256))).astype(np.float32)
+    imgs[0, 100, 7] = np.nan
+    imgs[0, 300, 200] = np.inf
+    imgs[1, 250, 130] = -np.inf
+    imgs[2, 40:44, 3] = np.nan
+    imgs[:, 400:403, :] += 150.0                                # detections below every special cell
+    dev = torch.from_numpy(imgs).cuda()
+    for alg in ("CA", "SOCA", "GOCA"):   # (std::nth_element over NaN is undefined behaviour in the reference's OS)
+        want_m, want_t = _oracle_batch(alg, imgs, 20, 5, 10, TAU[alg], want_thr=True)
+        out = ops.cfar(dev, alg, 20, 5, TAU[alg], k=10)
+        assert np.array_equal(out["mask"].cpu().numpy(), want_m), alg
+        out = ops.cfar(dev, alg, 20, 5, TAU[alg], k=10, want_thr=True)
+        assert np.array_equal(out["mask"].cpu().numpy(), want_m), alg
+        assert np.array_equal(out["thr"].cpu().numpy().view(np.uint32), want_t.view(np.uint32)), alg
+    assert want_m[0, 400:403, 7].any()                          # the beam recovers once the NaN left the window
+
+
+def test_lut_cache_is_per_context(gpu_ctx):
+    """Two contexts on one thread, different parameters, interleaved calls: each keeps its own table."""
+    from sonar_slam_b200 import _lib
+    imgs = synth.make_frames([4, 5])
+    dev = torch.from_numpy(imgs).cuda()
+    s2 = torch.cuda.Stream()
+    other = _lib.Context(0, s2.cuda_stream)
+    w65, _ = _oracle_batch("SOCA", imgs, 20, 5, 0, TAU["SOCA"], gate=65)
+    w90, _ = _oracle_batch("SOCA", imgs, 20, 5, 0, 3.5, gate=90)
+    for _ in range(3):
+        a = ops.cfar(dev, "SOCA", 20, 5, TAU["SOCA"], gate=65)
+        with torch.cuda.stream(s2):
+            b = ops.cfar(dev, "SOCA", 20, 5, 3.5, gate=90, ctx=other)
+        torch.cuda.synchronize()
+        assert np.array_equal(a["mask"].cpu().numpy(), w65) and np.array_equal(b["mask"].cpu().numpy(), w90)

@@ -59,3 +59,67 @@ def test_scatter_compute_gather_world2(n, window):
     for p in procs:
         p.join(60)
     assert ok == (True, True)
+
+
+# ------------------------------------------------------------------ config 5: backlog of independent scan matches
+def _fake_icp(src, tgt, guess, prm):
+    """Stand-in solver with the real one's signature: the packed 48-byte record is a checksum of the problem's own
+    clouds and guess, so a record that reached the wrong rank, chunk or slot changes the answer."""
+    n = src.shape[0]
+    out = torch.zeros((n, sdist.RESULT_WORDS), dtype=torch.int32)
+    if n == 0:
+        return out
+    out[:, 0] = (src.reshape(n, -1).sum(1) * 8).round().to(torch.int32)
+    out[:, 1] = (tgt.reshape(n, -1).sum(1) * 8).round().to(torch.int32)
+    out[:, 2] = (guess.reshape(n, -1)[:, 2] * 1000).round().to(torch.int32)
+    out[:, 9] = prm
+    return out
+
+
+def _pairs_worker(rank, world, port, P, chunks, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ns, nt = 5, 11
+    src = tgt = guess = None
+    if rank == 0:
+        g = torch.Generator().manual_seed(4)
+        src = torch.randint(0, 64, (P, ns, 2), generator=g).float() / 8
+        tgt = torch.randint(0, 64, (P, nt, 2), generator=g).float() / 8
+        guess = torch.eye(3).repeat(P, 1, 1)
+        guess[:, 0, 2] = torch.arange(P).float()
+    a = sdist.run_pair_backlog(P, ns, nt, 7, src, tgt, guess, chunks=chunks, icp_fn=_fake_icp, device="cpu")
+    shard = sdist.scatter_pairs(P, ns, nt, src, tgt, guess, device="cpu")
+    b = sdist.gather_pair_results(_fake_icp(*shard, 7), P)
+    if rank == 0:
+        want = _fake_icp(src, tgt, guess, 7)
+        q.put((bool(torch.equal(a, want)), bool(torch.equal(b, want)),
+               bool(torch.equal(sdist.unpack_results(a)["iterations"], want[:, 9]))))
+    else:
+        assert a is None and b is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P,chunks", [(37, 3), (3, 4), (64, 8), (1, 2)])
+def test_pair_backlog_scatter_solve_gather_world2(P, chunks):
+    plan = sdist.chunk_plan(P, 2, chunks)
+    assert sorted(i for r in plan for a, b in r for i in range(a, b)) == list(range(P))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pairs_worker, args=(r, 2, port, P, chunks, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+    assert ok == (True, True, True)
+
+
+def test_pack_unpack_results_roundtrip():
+    T = torch.randn(5, 3, 3)
+    res = dict(T=T, iterations=torch.arange(5, dtype=torch.int32), inliers=torch.arange(5, dtype=torch.int32) * 3,
+               status=torch.zeros(5, dtype=torch.int32))
+    back = sdist.unpack_results(sdist.pack_results(res))
+    assert torch.equal(back["T"], T) and torch.equal(back["inliers"], res["inliers"])

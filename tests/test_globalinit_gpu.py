@@ -66,10 +66,15 @@ def test_against_oracle(seed, ns, nt, K):
         poses[2] = gref.Pose2(float("nan"), 0.0, 0.0)
     got = cm.score(np.array([_row(p) for p in poses], np.float32))
     check = range(K) if K <= 64 else list(range(8)) + list(rng.integers(0, K, 40))
+    blas_differs = 0
     for k in check:
-        want = gref.cost_of_transform(grid, xmin, ymin, res, src, poses[k])
-        slack = gref.boundary_points(xmin, ymin, res, src, poses[k]) if np.isfinite(poses[k].x()) else 0
-        assert abs(int(got[k]) - want) <= slack, (k, int(got[k]), want, slack)
+        # integer work: EXACT against the cost with the float32 rounding spelled out (no slack) ...
+        want = gref.cost_of_transform(grid, xmin, ymin, res, src, poses[k], explicit=True)
+        assert int(got[k]) == want, (k, int(got[k]), want)
+        # ... which is what numpy's own float32 dot gives on this host (pinned on the reference-run fixture in
+        # tests/test_oracle_globalinit.py); counted here, since a BLAS kernel without FMA may round differently
+        blas_differs += int(gref.cost_of_transform(grid, xmin, ymin, res, src, poses[k]) != want)
+    print("poses where numpy's dot differs from the explicit float32 formula:", blas_differs, "of", len(check))
     assert got.min() >= -ns and got.max() <= 0
     if K > 4:
         assert got[1] == 0 and got[2] == 0

@@ -51,3 +51,21 @@ def test_boundary_point_counter():
     pts = np.array([[0.025, 0.0], [0.0249, 0.0], [1.0, 1.0]], np.float32)  # first: exactly on x.5 of the 0.05 grid
     n = gref.boundary_points(np.float32(0.0), np.float32(0.0), 0.05, pts, gref.Pose2())
     assert n >= 1 and n <= 2
+
+
+def test_explicit_float32_transform_equals_reference_costs(gold):
+    """The float32 dot product with its rounding spelled out (what the device kernel evaluates and what the exact
+    GPU test compares with) reproduces the costs of the reference-run fixture, and equals numpy's own `dot`
+    point for point on random clouds -- so "exact against the explicit formula" is "exact against the reference"."""
+    sp, tp = gref.Pose2(*gold["source_pose"]), gref.Pose2(*gold["target_pose"])
+    grid, xmin, ymin, res, _ = gref.target_grid(gold["target"], 0.5)
+    for x, want in zip(gold["xs"], gold["costs"]):
+        tr = tp.between(sp.compose(gref.Pose2(*x)))
+        assert gref.cost_of_transform(grid, xmin, ymin, res, gold["source"], tr, explicit=True) == want
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-40, 40, (20000, 2)).astype(np.float32)
+    diff = 0
+    for _ in range(20):
+        pose = gref.Pose2(*(rng.uniform(-1, 1, 3) * [5.0, 5.0, 3.0]))
+        diff += int((gref.transform_points(pts, pose) != gref.transform_points_explicit(pts, pose)).sum())
+    assert diff == 0, diff

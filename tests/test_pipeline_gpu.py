@@ -76,3 +76,97 @@ def test_frontend_both_icp_size_classes(gpu_ctx):
             assert got["iterations"][i] == want[i]["iterations"] and got["inliers"][i] == want[i]["inliers"], i
             dlt = np.abs(_pose(got["T"][i]) - _pose(want[i]["T"]))
             assert dlt[:2].max() < 1e-3 and dlt[2] < 1e-3, (i, dlt)
+
+
+def test_frontend_equals_node_chain_with_slam_sign_convention(gpu_ctx):
+    """The reference's two nodes, call by call: FeatureExtraction.callback (drop-in mirror, GPU kernels through the
+    host C ABI) publishes [p0, 0, p1] (feature_extraction.py:182); the SLAM node reads (x, -z) = (p0, -p1)
+    (slam_ros.py:169-170), keeps it as the keyframe cloud, builds the window submap with get_points and calls
+    compute_icp with the odometry guess.  The fused batch call must return the same edge for every frame --
+    i.e. it applies the same lateral sign flip (sfe_frontend_params.flip_lateral = 1)."""
+    from sonar_slam_b200.bruce_slam.feature_extraction import FeatureExtraction
+    from sonar_slam_b200.bruce_slam.slam import SLAM, Pose2
+    n = 9
+    d = synth.make_trajectory_frames(n, seed=8)
+    frames, poses = d["frames"].numpy(), d["poses_odom"]
+    fx = FeatureExtraction()
+    fx.init_node({"CFAR": {"Ntc": 40, "Ngc": 10, "Pfa": 0.1, "rank": 10, "alg": "SOCA"},
+                  "filter": {"threshold": 65, "resolution": 0.5, "radius": 1.0, "min_points": 5, "skip": 1},
+                  "compressed_images": False})
+    slam = SLAM()
+
+    class KF:
+        def __init__(self, points, pose):
+            self.points, self.pose = points, pose
+
+    edges = []
+    for i in range(n):
+        ping = synth.Ping(ping_id=i, image=frames[i], range_resolution=30.0 / 512, num_ranges=512, bearings=d["bearings"])
+        pts = fx.callback(ping)                                            # feature node
+        xyz = np.c_[pts[:, 0], np.zeros(len(pts)), pts[:, 1]].astype(np.float32)   # feature_extraction.py:182 (float32 msg)
+        points = np.c_[xyz[:, 0], -1 * xyz[:, 2]]                          # slam_ros.py:169-170
+        slam.keyframes.append(KF(points, Pose2(*poses[i])))
+        if i == 0:
+            edges.append(None)
+            continue
+        window = list(range(max(0, i - 3), i))
+        target = slam.get_points(window, i - 1)                            # slam.py:632-633
+        guess = slam.keyframes[i - 1].pose.between(slam.keyframes[i].pose)
+        if len(points) < 30 or len(target) < 30:
+            edges.append(None)
+            continue
+        edges.append(slam.compute_icp(points, target, guess))
+    fe = pipeline.FrontEnd(gpu_ctx, fx.device_maps(gpu_ctx, 512), max_frames=16, min_points=30)
+    got = fe.run_host(frames, poses, chunk_frames=4)
+    r = fe.results_dev()
+    xy = gpu_ctx.to_host(r["cloud_xy"], (n, r["cloud_stride"], 2), np.float32)
+    n_edges = 0
+    for i in range(n):
+        kf = slam.keyframes[i].points
+        assert np.array_equal(xy[i, :len(kf)], kf.astype(np.float32)), i   # the keyframe cloud, sign flip included
+        if edges[i] is None:
+            assert got["status"][i] == 7
+            continue
+        msg, pose = edges[i]
+        assert (msg == "success") == (got["status"][i] == 0), (i, msg, got["status"][i])
+        if msg == "success":
+            n_edges += 1
+            dlt = np.abs(_pose(got["T"][i]) - np.array([pose.x(), pose.y(), pose.theta()]))
+            assert dlt[:2].max() < 1e-3 and dlt[2] < 1e-3, (i, dlt)
+    assert n_edges >= n - 3
+    # with the odometry in the same (standard) frame as the flipped clouds the edges stay close to the odometry;
+    # without the flip the clouds are mirrored against it
+    off = pipeline.FrontEnd(gpu_ctx, fx.device_maps(gpu_ctx, 512), max_frames=16, min_points=30, flip_lateral=0)
+    raw = off.run_host(frames, poses, chunk_frames=4)
+    ro = off.results_dev()
+    xy0 = gpu_ctx.to_host(ro["cloud_xy"], (n, ro["cloud_stride"], 2), np.float32)
+    k = int(got["npoints"][2])
+    assert np.array_equal(xy0[2, :k] * np.array([1, -1], np.float32), xy[2, :k])
+    assert np.array_equal(raw["npoints"], got["npoints"])
+
+
+def test_oversize_frames_report_too_large_with_small_capacities(gpu_ctx):
+    """cap_source / cap_target below the first ICP size class: there is no second launch, so the one launch must
+    itself report clouds beyond the capacities (SFE_ICP_TOO_LARGE = 8) and hand the guess back."""
+    n = 8
+    d = synth.make_trajectory_frames(n, seed=3)
+    frames, poses = d["frames"].numpy(), d["poses_odom"]
+    geo = featx_ref.Geometry(30.0 / 512, 512, d["bearings"])
+    maps = _lib.Maps(gpu_ctx, geo.map_x, geo.map_y, 512, 512, geo.width, geo.height)
+    clouds, _ = pipeline_ref.run(frames, poses, geo, min_points=30)
+    sizes = np.array([len(c) for c in clouds])
+    cap_s = int(np.sort(sizes)[n // 2])                          # about half of the frames exceed it
+    fe = pipeline.FrontEnd(gpu_ctx, maps, max_frames=n, min_points=30, cap_source=cap_s, cap_target=1536)
+    got = fe.run_host(frames, poses, chunk_frames=3)
+    clouds, want = pipeline_ref.run(frames, poses, geo, min_points=30)
+    assert (sizes > cap_s).any() and (sizes[1:] <= cap_s).any()
+    for i in range(1, n):
+        if sizes[i] > cap_s:
+            assert got["status"][i] == 8 and got["iterations"][i] == 0 and got["inliers"][i] == 0, (i, got["status"][i])
+            assert np.array_equal(got["T"][i], want[i]["T"] if want[i]["status"] != 0 else
+                                  pipeline_ref.between(poses[i - 1], poses[i]))
+        else:
+            assert got["status"][i] == want[i]["status"], i
+    fe2 = pipeline.FrontEnd(gpu_ctx, maps, max_frames=n, min_points=30, cap_source=640, cap_target=200)
+    got2 = fe2.run_host(frames, poses, chunk_frames=8)
+    assert (got2["status"][2:] == 8).all()                       # every window submap exceeds 200 points
