@@ -178,11 +178,12 @@ typedef struct {
   float min_diff_trans;   /*                                            icp.yaml:27   0.1 */
   int smooth_length;      /* (0: differential checker off; <= 15)        icp.yaml:28     4 */
   int flags;              /* bit 0: MaxDist filter compares squared distance with maxDist itself
-                             bit 1: parity mode -- every sum over points (reference mean, pair means, cross-
-                                    covariance) is a SEQUENTIAL float32 sum in point order, the accumulation order of
-                                    the CPU oracle (oracle/icp_ref.c); results are then bit-identical to it.  Default
-                                    (bit clear): float32 terms accumulated in float64, order-independent and ~1e-4
-                                    closer to exact arithmetic; a few per cent faster. */
+                             bit 1: accumulate the sums over points (reference mean, pair means, cross-covariance) in
+                                    float64, order-independent.  DEFAULT (bit clear): every such sum is a SEQUENTIAL
+                                    float32 sum in point order, the accumulation order of the CPU oracle
+                                    (oracle/icp_ref.c) -- results are bit-identical to it.  The float64 mode is a few
+                                    per cent faster and closer to exact arithmetic, but differs from the float32 chain by
+                                    up to ~2e-3 m on ill-conditioned scans (tests/test_icp_parity_gpu.py). */
 } sfe_icp_params;
 SFE_API void sfe_icp_params_default(sfe_icp_params *p);
 
@@ -265,6 +266,12 @@ SFE_API int sfe_frontend_run_dev(sfe_frontend *fe, const uint8_t *frames_dev, co
 SFE_API int sfe_frontend_results_dev(const sfe_frontend *fe, const float **T, const int32_t **iters,
                                      const int32_t **inliers, const int32_t **status, const float **cloud_xy,
                                      const int32_t **cloud_count, int32_t *cloud_stride);
+/* Continuation across calls (the window submap stays resident on the device).  With carry enabled,
+ * every call keeps the clouds and odometry poses of its last `window` frames on the device, and the next call on
+ * this handle continues the sequence: its first frames are matched against the carried frames (frame 0 included),
+ * exactly as if the batches had been one call -- a replay can be fed in pieces of any size without a cold window at
+ * every seam.  enable = 0 (the default) drops the carried frames: every call starts cold (frame 0 SFE_ICP_SKIPPED). */
+SFE_API int sfe_frontend_set_carry(sfe_frontend *fe, int enable);
 /* Optional per-stage device timing (CUDA events on the launch stream around every stage's kernels).
  * get_timing synchronises, adds the intervals recorded since the last call to running totals and
  * returns the totals: stage_ms[SFE_FE_STAGES], stage_calls[SFE_FE_STAGES] (may be NULL). */
@@ -306,6 +313,24 @@ SFE_API int sfe_costmap_score_host(sfe_ctx *ctx, const sfe_costmap *cm, const fl
 /* device flavour: source cloud, transforms and costs in device memory, asynchronous on the context's stream */
 SFE_API int sfe_costmap_score_dev(sfe_ctx *ctx, const sfe_costmap *cm, const float *source_xy_dev, int n_source,
                                   const float *transforms_dev, int n_candidates, int32_t *cost_dev);
+
+/* ------------------------------------------------------------------ loop-closure target pre-filter (next row N3)
+ * SLAM.initialize_nonsequential_scan_matching, slam.py:878-899: keep the points of the accumulated target cloud that
+ * lie inside the field of view of at least one of the n_frames source keyframes, range and aperture inflated by the
+ * keyframe's pose uncertainty.  Per source keyframe k the caller passes (computed on the host exactly like
+ * slam.py:883-888):
+ *   inv_T[k]          6 floats {r00, r01, r10, r11, tx, ty} of pose.inverse().matrix().astype(float32)
+ *                     (Keyframe.transform_points, slam_objects.py:195)
+ *   range_bound[k]    translation_std * 5.0 + oculus.max_range                       (float64)
+ *   bearing_bound[k]  rotation_std * 5.0 + oculus.horizontal_aperture * 0.5          (float64)
+ * pts: float32 [n][2] (global frame); sel[i] = 1 iff for some k the point moved into keyframe k's frame has
+ * float32 norm < range_bound[k] and |float32 atan2| < bearing_bound[k]  (the `sel |= sel_i` loop, slam.py:879-895). */
+SFE_API int sfe_fov_select_dev(sfe_ctx *ctx, const float *pts_dev, int n, const float *inv_T_dev,
+                               const double *range_bound_dev, const double *bearing_bound_dev, int n_frames,
+                               uint8_t *sel_dev);
+SFE_API int sfe_fov_select_host(sfe_ctx *ctx, const float *pts_host, int n, const float *inv_T_host,
+                                const double *range_bound_host, const double *bearing_bound_host, int n_frames,
+                                uint8_t *sel_host);
 
 #ifdef __cplusplus
 }

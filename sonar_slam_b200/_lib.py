@@ -96,11 +96,14 @@ _EXTRA_SIGNATURES = {
     "sfe_copy_to_host": [c_void_p, c_void_p, c_void_p, ctypes.c_uint64],
     "sfe_frontend_create": [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(c_void_p)],
     "sfe_frontend_set_timing": [c_void_p, c_int],
+    "sfe_frontend_set_carry": [c_void_p, c_int],
     "sfe_frontend_get_timing": [c_void_p, c_void_p, c_void_p],
     "sfe_frontend_run_dev": [c_void_p, c_void_p, c_void_p, c_int],
     "sfe_frontend_results_dev": [c_void_p] + [ctypes.POINTER(c_void_p)] * 6 + [ctypes.POINTER(ctypes.c_int32)],
     "sfe_frontend_run_host": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p],
+    "sfe_fov_select_dev": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "sfe_fov_select_host": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "sfe_icp_host": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                      c_void_p, c_void_p],
 }

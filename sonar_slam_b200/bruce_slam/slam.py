@@ -69,6 +69,8 @@ class SLAM(object):
         self.icp = pcl.ICP()
         self.icp_ssm = pcl.ICP()
         self.keyframes = []
+        # the two OculusProperty fields the loop-closure pre-filter reads (sonar.py:151,158)
+        self.oculus = type("OculusProperty", (), {"max_range": 30.0, "horizontal_aperture": np.radians(130.0)})()
 
     # ---- slam.py:294-323
     def compute_icp(self, source_points, target_points, guess=None):
@@ -198,6 +200,35 @@ class SLAM(object):
         if result.success:
             out["estimated_source_pose"] = source_pose.compose(Pose2(*result.x))
         return out
+
+    # ---- slam.py:876-899 (inside initialize_nonsequential_scan_matching): field-of-view pre-filter of the targets
+    def select_targets_in_fov(self, target_points, target_keys, source_frames):
+        """Keep the target points (global frame) that at least one of `source_frames` could have seen, range and
+        aperture inflated by 5 sigma of that keyframe's pose (keyframes need .pose and .cov).  The per-keyframe
+        bounds are the reference's host expressions; the per-point test runs on the GPU (sfe_fov_select_host).
+        Returns (target_points[sel], target_keys[sel], sel)."""
+        target_points = np.ascontiguousarray(target_points, np.float32)
+        inv_T, rb, bb = [], [], []
+        for source_frame in source_frames:
+            pose = self.keyframes[source_frame].pose
+            cov = self.keyframes[source_frame].cov
+            translation_std = np.sqrt(np.max(np.linalg.eigvals(cov[:2, :2])))
+            rotation_std = np.sqrt(cov[2, 2])
+            rb.append(translation_std * 5.0 + self.oculus.max_range)
+            bb.append(rotation_std * 5.0 + self.oculus.horizontal_aperture * 0.5)
+            T = pose.inverse().matrix().astype(np.float32)  # Keyframe.transform_points, slam_objects.py:195
+            inv_T.append([T[0, 0], T[0, 1], T[1, 0], T[1, 1], T[0, 2], T[1, 2]])
+        sel = np.zeros(len(target_points), np.uint8)
+        if len(target_points) and len(inv_T):
+            ctx = _lib.default_context()
+            inv_T = np.ascontiguousarray(inv_T, np.float32)
+            rb, bb = np.ascontiguousarray(rb, np.float64), np.ascontiguousarray(bb, np.float64)
+            _lib.check(ctx.lib.sfe_fov_select_host(ctx.handle, _lib.ptr(target_points), len(target_points),
+                                                   _lib.ptr(inv_T), _lib.ptr(rb), _lib.ptr(bb), len(inv_T),
+                                                   _lib.ptr(sel)), "sfe_fov_select_host")
+        sel = sel.astype(bool)
+        keys = None if target_keys is None else np.asarray(target_keys)[sel]
+        return target_points[sel], keys, sel
 
     # ---- slam.py:229-292 for (points, pose) keyframe tuples
     def get_points(self, frames=None, ref_frame=None, return_keys=False):

@@ -491,70 +491,53 @@ __global__ void __launch_bounds__(CF_W, 5)
 // uint8 streaming kernel for the node's configuration (CFAR + amplitude gate fused, feature_extraction.py:223-224):
 // FOUR beams per thread, SIMD inside 32-bit registers.  With the gate on, a cell can only be a detection when
 // x >= g_min = min_S M[S] (M = the pass table of cfar_u8_lut_kernel; g_min is the gate for the shipped parameters),
-// which is rare in sonar imagery (Rayleigh speckle: ~0.2 % of the cells).  So the per-cell work is only what keeps
-// the window sums current, and the table look-up / compare / bit set runs in a rarely taken branch:
+// which holds for a few per cent of the cells of a sonar image (speckle tail + echoes).  The per-cell work is only
+// what keeps the window statistic current; the table look-up / compare / bit set is done per CANDIDATE:
 //   * one LDS.32 brings the new cells of 4 adjacent beams (bytes); the raw words also form the cell ring;
 //   * window sums (<= 20*255 < 2^16) live as 16-bit lanes, two beams per register: PRMT spreads the bytes of the
 //     entering and the leaving cell to 16-bit lanes, one IADD3 per beam pair updates the sums (lanes cannot carry
-//     into each other: every lane stays in [0, 5100]); a 32-deep register delay line yields the leading sum;
+//     into each other: every lane stays in [0, 5100]); a 32-deep register delay line yields the leading sum and
+//     VIMNMX.U16x2 the SOCA / GOCA statistic;
 //   * "does any of the 4 cells under test reach g_min" is two integer instructions on the packed bytes
-//     (((x + k) | x) & 0x80808080, k = (128 - g_min) * 0x01010101); only then VIMNMX.U16x2 forms min/max(lead, lag)
-//     and the table M[S] is consulted per beam, setting bits (atomicOr) / bytes in a zero-initialised shared tile.
-// ~2.5 instructions per cell instead of ~9 (cuobjdump -sass: profiles/), all-integer, exact: identical to the
-// table kernel by construction (the branch is a necessary condition; the decision is the same table compare).
+//     (((x + k) | x) & 0x80808080, k = (128 - g_min) * 0x01010101); a thread whose word qualifies parks
+//     (cells, statistic) in its own shared-memory slot of that row with predicated stores and sets a bit in a
+//     16-bit row mask -- the 16-row block is branch-free;
+//   * after the block every thread walks ITS OWN row mask and decides the parked cells against the table M[S]
+//     (atomicOr into a zero-initialised bit tile / byte stores into a mask tile).  The divergence is per lane, not
+//     per row: an echo that crosses a warp's 128 beams on 60 different rows costs each lane its own one or two
+//     rows, not the warp 60 excursions.
+// ~3.5 instructions per cell instead of ~9 for the table kernel, all-integer, exact: identical to the table
+// kernel by construction (the gate test is a necessary condition; the decision is the same table compare).
 // A strip is 512 beams (128 threads x 4); 16-row chunks arrive by TMA as two [16 x 256] boxes per stage.  Block b
 // consumes chunk b (newest cell rn = 16 b + i) and decides cell r = rn - 25, so every block touches ONE tile.
 constexpr int CG_BEAMS = 4;
 constexpr int CG_W = CF_W * CG_BEAMS;  // beams per strip
 constexpr int CG_NS = 4;               // input ring depth
-constexpr int CG_GMIN_LO = 16;         // below this the "rare branch" is not rare: use the table kernel
+constexpr int CG_GMIN_LO = 16;         // below this nearly every word qualifies: use the table kernel
 
 struct CfarStepG {
   uint32_t xr[CF_RING];                // cells, 4 beams per word
   uint32_t wl[CF_RING], wh[CF_RING];   // window sums W[rn - a]: beams 0,1 / beams 2,3 as 16-bit lanes
   uint32_t w_lo, w_hi;                 // W[rn - 1]
+  uint32_t hit;                        // rows of the current block with a parked candidate word
 };
 
 // shared-memory layout of cfar_u8_gate4_kernel (dynamic): tile [CG_NS][2][16][256] | obits [2][16][16] |
-// full_bar [CG_NS] | lut [lut_n padded to 8] | omask [2][16][512] (MASK only)
+// full_bar [CG_NS] | parked statistic [16][128] uint2 | parked cells [16][128] u32 | lut [lut_n padded to 8] |
+// omask [2][16][512] (MASK only)
 constexpr size_t CG_OFF_OBITS = (size_t)CG_NS * CF_CH * CG_W;
 constexpr size_t CG_OFF_BAR = CG_OFF_OBITS + sizeof(uint32_t) * 2 * CF_CH * (CG_W / 32);
-constexpr size_t CG_OFF_LUT = CG_OFF_BAR + 64;
+constexpr size_t CG_OFF_RECS = CG_OFF_BAR + 64;
+constexpr size_t CG_OFF_RECX = CG_OFF_RECS + sizeof(uint2) * CF_CH * CF_W;
+constexpr size_t CG_OFF_LUT = CG_OFF_RECX + sizeof(uint32_t) * CF_CH * CF_W;
 __host__ __device__ __forceinline__ size_t cg_off_omask(int lut_n) {
   return CG_OFF_LUT + ((sizeof(uint16_t) * (size_t)((lut_n + 7) / 8 * 8) + 15) & ~size_t(15));
 }
 extern __shared__ __align__(128) unsigned char cg_smem[];
 
-// The rare branch: decide the four cells of one row.  `row` = ob * 16 + i indexes the output tiles.
-template <int ALG, bool MASK, bool BITS>
-__device__ __noinline__ void cfar_gate_hit(const uint32_t xc4, const uint32_t lead_lo, const uint32_t lead_hi,
-                                           const uint32_t lag_lo, const uint32_t lag_hi, const int row,
-                                           const int lut_n, const int tid, const int nvalid) {
-  const uint16_t *lut = reinterpret_cast<const uint16_t *>(cg_smem + CG_OFF_LUT);
-  uint32_t s_lo, s_hi;
-  if (ALG == SFE_CFAR_CA) s_lo = lead_lo + lag_lo, s_hi = lead_hi + lag_hi;  // <= 10200 per lane
-  else if (ALG == SFE_CFAR_SOCA) s_lo = __vminu2(lead_lo, lag_lo), s_hi = __vminu2(lead_hi, lag_hi);
-  else s_lo = __vmaxu2(lead_lo, lag_lo), s_hi = __vmaxu2(lead_hi, lag_hi);
-  uint32_t set = 0;
-#pragma unroll
-  for (int k = 0; k < CG_BEAMS; ++k) {
-    const int x = (int)((xc4 >> (8 * k)) & 255u);
-    const int S = (int)(((k < 2 ? s_lo : s_hi) >> (16 * (k & 1))) & 0xffffu);
-    if (k < nvalid && x >= (int)lut[S]) set |= 1u << k;
-  }
-  if (set == 0) return;
-  if (BITS)
-    atomicOr(reinterpret_cast<uint32_t *>(cg_smem + CG_OFF_OBITS) + row * (CG_W / 32) + (tid >> 3),
-             set << ((tid & 7) * CG_BEAMS));
-  if (MASK)  // bytes 0/1 of the four beams: spread the 4 bits to 4 bytes
-    *reinterpret_cast<uint32_t *>(cg_smem + cg_off_omask(lut_n) + (size_t)row * CG_W + CG_BEAMS * tid) =
-        (set & 1u) | ((set & 2u) << 7) | ((set & 4u) << 14) | ((set & 8u) << 21);
-}
-
-template <int ALG, bool MASK, bool BITS, bool EDGE, int J>
+template <int ALG, int J>
 __device__ __forceinline__ void cfar_step_g(CfarStepG &s, const uint32_t xn4, const uint32_t gate_add,
-                                            const int lut_n, const int ob, const int R, const int r, const int tid,
-                                            const int nvalid) {
+                                            uint2 (*rec_s)[CF_W], uint32_t (*rec_x)[CF_W], const int tid) {
   constexpr int I = J % CF_CH;
   const uint32_t x20 = s.xr[(J + CF_RING - CF_T) % CF_RING];
   const uint32_t xc4 = s.xr[(J + CF_RING - CF_HALF) % CF_RING];
@@ -565,11 +548,16 @@ __device__ __forceinline__ void cfar_step_g(CfarStepG &s, const uint32_t xn4, co
   s.w_lo = lag_lo, s.w_hi = lag_hi;
   s.wl[J % CF_RING] = lag_lo, s.wh[J % CF_RING] = lag_hi;
   s.xr[J % CF_RING] = xn4;
+  uint32_t s_lo, s_hi;
+  if (ALG == SFE_CFAR_CA) s_lo = lead_lo + lag_lo, s_hi = lead_hi + lag_hi;  // <= 10200 per lane
+  else if (ALG == SFE_CFAR_SOCA) s_lo = __vminu2(lead_lo, lag_lo), s_hi = __vminu2(lead_hi, lag_hi);
+  else s_lo = __vmaxu2(lead_lo, lag_lo), s_hi = __vmaxu2(lead_hi, lag_hi);
   // any of the four cells under test >= g_min?  (a carry out of a byte only happens when that byte already
-  // qualifies, so the any-test is exact; which bytes qualify is settled in cfar_gate_hit)
-  if (((xc4 + gate_add) | xc4) & 0x80808080u) {
-    if (!EDGE || (r >= CF_HALF && r < R - CF_HALF))
-      cfar_gate_hit<ALG, MASK, BITS>(xc4, lead_lo, lead_hi, lag_lo, lag_hi, ob * CF_CH + I, lut_n, tid, nvalid);
+  // qualifies, so the any-test is exact; which bytes pass is settled against the table after the block)
+  if (((xc4 + gate_add) | xc4) & 0x80808080u) {  // (predicated stores, no branch)
+    rec_s[I][tid] = make_uint2(s_lo, s_hi);
+    rec_x[I][tid] = xc4;
+    s.hit |= 1u << I;
   }
 }
 
@@ -577,13 +565,15 @@ template <int ALG, bool MASK, bool BITS, bool EDGE, int Q>
 __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][CF_CH][CG_W / 2],
                                                uint32_t (*obits)[CF_CH][CG_W / 32], uint8_t (*omask)[CF_CH][CG_W],
                                                uint64_t *full_bar, const CUtensorMap *in_map,
-                                               const int lut_n, const CfarParams &p, const int blk,
+                                               const uint16_t *__restrict__ lut, const CfarParams &p, const int blk,
                                                const int nchunks, const int tid, const int f, const int col0,
                                                const uint32_t gate_add, const int nvalid) {
   const int r0 = blk * CF_CH - CF_HALF;  // first output row of this block
   constexpr int ob = Q & 1;
   const int st = blk & (CG_NS - 1);
   const bool has = EDGE ? (blk < nchunks) : true;
+  uint2(*rec_s)[CF_W] = reinterpret_cast<uint2(*)[CF_W]>(cg_smem + CG_OFF_RECS);
+  uint32_t(*rec_x)[CF_W] = reinterpret_cast<uint32_t(*)[CF_W]>(cg_smem + CG_OFF_RECX);
   uint32_t xin[CF_CH];
   if (has) {
     mbar_wait(&full_bar[st], (blk / CG_NS) & 1);
@@ -594,11 +584,34 @@ __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][
 #pragma unroll
     for (int i = 0; i < CF_CH; ++i) xin[i] = 0u;  // below the image: zero cells (never decide anything)
   }
-#define SFE_STEP(I) \
-  cfar_step_g<ALG, MASK, BITS, EDGE, Q * CF_CH + I>(s, xin[I], gate_add, lut_n, ob, p.R, r0 + I, tid, nvalid);
+  s.hit = 0u;
+#define SFE_STEP(I) cfar_step_g<ALG, Q * CF_CH + I>(s, xin[I], gate_add, rec_s, rec_x, tid);
   SFE_STEP(0) SFE_STEP(1) SFE_STEP(2) SFE_STEP(3) SFE_STEP(4) SFE_STEP(5) SFE_STEP(6) SFE_STEP(7)
   SFE_STEP(8) SFE_STEP(9) SFE_STEP(10) SFE_STEP(11) SFE_STEP(12) SFE_STEP(13) SFE_STEP(14) SFE_STEP(15)
 #undef SFE_STEP
+  // ---- the parked candidates of this thread: the reference's compare, via the table (own slots: no barrier)
+  uint32_t hit = s.hit;
+  while (hit) {
+    const int i = __ffs(hit) - 1;
+    hit &= hit - 1;
+    const int r = r0 + i;
+    if (EDGE && !(r >= CF_HALF && r < p.R - CF_HALF)) continue;  // border rows stay 0
+    const uint2 sv = rec_s[i][tid];
+    const uint32_t xc4 = rec_x[i][tid];
+    uint32_t set = 0;
+#pragma unroll
+    for (int k = 0; k < CG_BEAMS; ++k) {
+      const int x = (int)((xc4 >> (8 * k)) & 255u);
+      const int S = (int)(((k < 2 ? sv.x : sv.y) >> (16 * (k & 1))) & 0xffffu);
+      if (k < nvalid && x >= (int)lut[S]) set |= 1u << k;
+    }
+    if (set) {
+      if (BITS) atomicOr(&obits[ob][i][tid >> 3], set << ((tid & 7) * CG_BEAMS));
+      if (MASK)  // bytes 0/1 of the four beams: spread the 4 bits to 4 bytes
+        *reinterpret_cast<uint32_t *>(&omask[ob][i][CG_BEAMS * tid]) =
+            (set & 1u) | ((set & 2u) << 7) | ((set & 4u) << 14) | ((set & 8u) << 21);
+    }
+  }
   __syncthreads();  // every thread has read tile[st]; the block's detections are in obits[ob] / omask[ob]
   if (tid == 0 && blk + CG_NS < nchunks) {
     mbar_arrive_expect_tx(&full_bar[st], CF_CH * CG_W);
@@ -639,7 +652,7 @@ __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][
 }
 
 template <int ALG, bool MASK, bool BITS>
-__global__ void __launch_bounds__(CF_W, MASK ? 3 : 4)
+__global__ void __launch_bounds__(CF_W, MASK ? 2 : 3)
     cfar_u8_gate4_kernel(const __grid_constant__ CUtensorMap in_map, CfarParams p, const uint16_t *__restrict__ lut_g,
                          const int lut_n, const uint32_t gate_add) {
   uint8_t(*tile)[2][CF_CH][CG_W / 2] = reinterpret_cast<uint8_t(*)[2][CF_CH][CG_W / 2]>(cg_smem);
@@ -673,7 +686,7 @@ __global__ void __launch_bounds__(CF_W, MASK ? 3 : 4)
   CfarStepG s;
 #pragma unroll
   for (int i = 0; i < CF_RING; ++i) s.xr[i] = 0u, s.wl[i] = 0u, s.wh[i] = 0u;
-  s.w_lo = 0u, s.w_hi = 0u;
+  s.w_lo = 0u, s.w_hi = 0u, s.hit = 0u;
   const int nvalid = min(max(p.B - (col0 + CG_BEAMS * tid), 0), CG_BEAMS);
   // block b: newest cells rn = 16 b .. 16 b + 15, decides rows rn - 25; the last decided row is R - 1
   const int nblk = (R + CF_HALF + CF_CH - 1) / CF_CH;
@@ -685,7 +698,7 @@ __global__ void __launch_bounds__(CF_W, MASK ? 3 : 4)
         const int r0 = blk * CF_CH - CF_HALF;
         const bool interior = (r0 >= CF_HALF) && (r0 + CF_CH - 1 < R - CF_HALF) && blk < nchunks;
 #define SFE_BLOCK(EDGE_, Q_) \
-  cfar_block16_g<ALG, MASK, BITS, EDGE_, Q_>(s, tile, obits, omask, full_bar, &in_map, lut_n, p, blk, nchunks, tid, f, col0, gate_add, nvalid)
+  cfar_block16_g<ALG, MASK, BITS, EDGE_, Q_>(s, tile, obits, omask, full_bar, &in_map, lut, p, blk, nchunks, tid, f, col0, gate_add, nvalid)
         if (interior) {
           if (q == 0) SFE_BLOCK(false, 0); else SFE_BLOCK(false, 1);
         } else {

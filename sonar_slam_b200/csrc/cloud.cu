@@ -214,42 +214,40 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
         facc[a] = sum;
       }
       __syncthreads();
-      // leaves in key order (= depth-first order): every thread owns a contiguous run of cells
+      // leaves in key order (= depth-first order).  Every thread owns a contiguous run of MEMBERS of the sorted list
+      // (balanced: occupied leaves cluster in a small part of the 4^D cell table, so a split by cell range left a
+      // handful of threads with all the work -- 25 % of this kernel's instructions at 3 active lanes); a member is
+      // a leaf head when it is the first of its cell (D <= 7: one leaf per cell) or of its run of equal keys.
       {
-        const int per = (ncells + nthr - 1) / nthr;
-        const int c0 = min(tid * per, ncells), c1 = min(c0 + per, ncells);
+        const int per = (n + nthr - 1) / nthr;
+        const int a0 = min(tid * per, n), a1 = min(a0 + per, n);
+        auto is_head = [&](int a) -> bool {
+          if (wide) return a == 0 || key32[sidx[a]] != key32[sidx[a - 1]];
+          return a == (int)cstart[key16[sidx[a]]];
+        };
         int mine = 0;
-        if (wide) {
-          for (int q = cstart[c0]; q < cstart[c1]; ++q)
-            mine += (q == cstart[c0]) || key32[sidx[q]] != key32[sidx[q - 1]];
-        } else {
-          for (int c = c0; c < c1; ++c) mine += cstart[c + 1] > cstart[c];
-        }
+        for (int a = a0; a < a1; ++a) mine += is_head(a) ? 1 : 0;
         int total;
         int rank = block_exclusive_scan(mine, scan, total);
-        int q = cstart[c0];
-        const int qend = cstart[c1];
-        int c = c0;
-        while (q < qend) {
+        for (int a = a0; a < a1; ++a) {
+          if (!is_head(a)) continue;
           int e0;
           if (wide) {
-            const unsigned kq = key32[sidx[q]];
-            e0 = q + 1;
-            while (e0 < qend && key32[sidx[e0]] == kq) ++e0;
+            const unsigned ka = key32[sidx[a]];
+            e0 = a + 1;
+            while (e0 < n && key32[sidx[e0]] == ka) ++e0;
           } else {
-            while (cstart[c + 1] <= q) ++c;
-            e0 = cstart[c + 1];
+            e0 = cstart[(int)key16[sidx[a]] + 1];
           }
           float best = 3.402823466e+38f;
-          int med = q;
-          for (int m = q; m < e0; ++m)
+          int med = a;
+          for (int m = a; m < e0; ++m)
             if (facc[m] < best) best = facc[m], med = m;
           const int idx = sidx[med];
           const size_t dst = (size_t)(o + rank);
           for (int d = 0; d < b.dim; ++d) b.out_pts[dst * b.dim + d] = pts[(size_t)idx * b.dim + d];
           b.out_idx[dst] = idx;
           ++rank;
-          q = e0;
         }
         if (tid == 0) b.out_count[cl] = total;
       }

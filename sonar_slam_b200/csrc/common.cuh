@@ -20,6 +20,7 @@ void set_error(const char *fmt, ...);  // thread-local message behind sfe_last_e
     cudaError_t e_ = (call);                                                                \
     if (e_ != cudaSuccess) {                                                                \
       sfe::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      (void)cudaGetLastError(); /* do not leave the error for an unrelated later call */   \
       return SFE_ERR_CUDA;                                                                  \
     }                                                                                       \
   } while (0)
@@ -56,7 +57,6 @@ struct sfe_ctx {
   // thread-local statics: a new context may get a recycled device address, two contexts may share a thread)
   double cfar_lut_key[6] = {-1, 0, 0, 0, 0, 0};  // parameters of the table held in scratch[SCR_CFAR_LUT]
   const void *cfar_lut_buf = nullptr;            // ... and the buffer it was uploaded to (null = none)
-  size_t icp_attr_smem[4] = {0, 0, 0, 0};        // cudaFuncAttributeMaxDynamicSharedMemorySize set per ICP instantiation
   struct OccEntry { size_t smem; int threads, per_sm, variant; } icp_occ[8] = {};
   int icp_occ_next = 0;
 };

@@ -260,6 +260,80 @@ __device__ __forceinline__ int nn_search(const GridView &g, float qx, float qy, 
   return exact;
 }
 
+// ---------------------------------------------------------------- warp-cooperative search
+// The same search as nn_search, run by ALL 32 lanes of a warp for ONE query (arguments are warp-uniform).  Long
+// searches -- a scan point far from every wall has to look at hundreds of candidates -- are the ones a warp should
+// share: with one query per lane such a lane keeps its warp busy for the whole scan while the other lanes idle
+// (ncu on 2 000 x 20 000-point problems: 7 of 32 lanes active on average, 2-5 in the candidate loops).
+// Block scan: the rows of the (2k+1)^2 block are dealt to four groups of eight lanes, each group strides its row's
+// contiguous point range; a butterfly picks the closest candidate, and ties (equal float32 distance at different
+// positions, within a lane or across lanes) fall back to the exact lowest-original-index rule.  Blocks are nested,
+// so the best of the last block scanned is the best of everything scanned.  Result = nn_search's, on every lane.
+__device__ __forceinline__ void nn_scan_block_warp(const GridView &g, int cx, int cy, int k, float qx, float qy,
+                                                   NNResult &r) {
+  const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+  const int xa = max(cx - k, 0), xb = min(cx + k, g.nx - 1);
+  const int ya = max(cy - k, 0), yb = min(cy + k, g.ny - 1);
+  NNResult m;
+  m.d2 = INFINITY, m.pos = -1, m.tie = 0;
+  for (int y = ya + grp; y <= yb; y += 4) {
+    const int s = g.cstart[y * g.nx + xa], e = g.cstart[y * g.nx + xb + 1];
+    for (int p = s + sub; p < e; p += 8) {
+      const float2 t = g.pts[p];
+      nn_update(dist2_rn(qx - t.x, qy - t.y), p, m);
+    }
+  }
+  // closest over the warp; a tie is two different positions at the winning distance
+  float d = m.d2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d = fminf(d, __shfl_xor_sync(0xffffffffu, d, o));
+  const unsigned win = __ballot_sync(0xffffffffu, m.d2 == d && m.pos >= 0);
+  if (win == 0u) {  // nothing in the block
+    r.d2 = INFINITY, r.pos = -1, r.tie = 0;
+    return;
+  }
+  const int first = __ffs(win) - 1;
+  const int pos = __shfl_sync(0xffffffffu, m.pos, first);
+  const unsigned other = __ballot_sync(0xffffffffu, m.d2 == d && m.pos >= 0 && (m.pos != pos || m.tie));
+  r.d2 = d, r.pos = pos, r.tie = other != 0u;
+}
+
+// returns 1: r = exact nearest neighbour (if any within max_d2); 0: every point is farther than sqrt(stop_d2)
+// (r is then not the NN).  `r` may carry a candidate from an earlier partial scan of the block of radius k_done.
+__device__ __forceinline__ int nn_search_warp(const GridView &g, float qx, float qy, float max_d2, float stop_d2,
+                                              int k_done, NNResult &r) {
+  if (g.n <= 0) return 1;
+  const int cx = grid_cell_coord(qx, g.ox, g.inv_cell, g.nx), cy = grid_cell_coord(qy, g.oy, g.inv_cell, g.ny);
+  const int kmax = max(g.nx, g.ny);
+  const float lim = fminf(max_d2, stop_d2);
+  int k = k_done;
+  int exact = -1;
+  while (exact < 0) {
+    if (k >= 0) {
+      const float b2 = nn_block_bound2(g, qx, qy, cx, cy, k);
+      if (b2 == INFINITY || b2 > r.d2 || b2 > max_d2) {
+        exact = 1;
+      } else if (b2 > stop_d2) {
+        exact = 0;
+      } else if (r.pos >= 0 && r.d2 <= lim) {
+        const float d = sqrtf(r.d2);
+        int kk = (int)(d * g.inv_cell * 1.0001f) + 1;
+        kk = min(max(kk, k + 1), kmax);
+        nn_scan_block_warp(g, cx, cy, kk, qx, qy, r);
+        k = kk;
+        continue;
+      } else if (k >= kmax) {
+        exact = 1;
+      }
+      if (exact >= 0) break;
+    }
+    k = k < 0 ? 0 : (k == 0 ? 1 : min(2 * k, kmax));
+    nn_scan_block_warp(g, cx, cy, k, qx, qy, r);
+  }
+  if (exact == 1 && r.tie) nn_resolve_tie(g, cx, cy, k, qx, qy, r);  // rare; every lane computes the same answer
+  return exact;
+}
+
 // exact nearest neighbour of (qx,qy); accepted only when d2 <= max_d2
 __device__ __forceinline__ NNResult nn_query(const GridView &g, float qx, float qy, float max_d2) {
   NNResult r;

@@ -17,6 +17,8 @@
 //   order: deterministic)  ->  closed-form 2-D rotation and translation, T_iter update and the
 //   Counter / Differential checkers on one thread.
 // CTAs are persistent over the problem list (batch of keyframe pairs / of initial guesses).
+#include <mutex>
+
 #include "grid.cuh"
 
 namespace sfe {
@@ -53,7 +55,7 @@ struct IcpBatch {
   float cell_scale;  // grid cell = cell_scale * sqrt(area / n)
   sfe_icp_params prm;
   uint16_t *orig_ws;  // [slots][nt_max]
-  float4 *seq_ws;     // [slots][ns_max] per-point terms of the sequential sums (flags bit 1 only)
+  float4 *seq_ws;     // [slots][ns_max] per-point terms of the sequential sums (unless flags bit 1)
   int slot_by_smid;   // workspace slot = %smid (one CTA per SM, one CTA per problem) instead of blockIdx.x
 };
 
@@ -156,7 +158,7 @@ struct IcpShared {  // small fixed-size part of the shared state
   float wred[4 * 16];      // per-warp partials of the bounding-box / maximum reductions
   float hq_w[ICP_HIST], hq_z[ICP_HIST], ht_x[ICP_HIST], ht_y[ICP_HIST];
   int hn;
-  float seq[4];               // results of the sequential sums (flags bit 1)
+  float seq[4];               // results of the sequential sums
   int cnx, cny;               // coarse occupancy grid (ICP_COARSE x ICP_COARSE fine cells per coarse cell)
   uint32_t coarse[ICP_COARSE_WORDS];
 };
@@ -210,8 +212,8 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
   return __uint_as_float(prefix);
 }
 
-// exact sequential float32 sum of n values p[0], p[stride], ... in index order (flags bit 1: the accumulation
-// order of oracle/icp_ref.c).  The loads of eight terms are issued together; the adds stay in order.
+// exact sequential float32 sum of n values p[0], p[stride], ... in index order (the accumulation order of
+// oracle/icp_ref.c; default mode).  The loads of eight terms are issued together; the adds stay in order.
 __device__ __forceinline__ float seq_sum_f32(const float *p, int n, int stride) {
   float s = 0.f;
   int i = 0;
@@ -264,9 +266,11 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   const float max_d2 = __fmul_rn(prm.matcher_max_dist, prm.matcher_max_dist);
   const float out_d2 = (prm.flags & 1) ? prm.outlier_max_dist : __fmul_rn(prm.outlier_max_dist, prm.outlier_max_dist);
   const int smooth = min(prm.smooth_length, ICP_HIST - 1);
-  // flags bit 1: every sum over points is a sequential float32 sum in point order, as in oracle/icp_ref.c (the
-  // parity mode: results are bit-identical to the oracle); default: float32 terms accumulated in float64.
-  const bool seq = (prm.flags & 2) != 0;
+  // Default: every sum over points is a sequential float32 sum in point order, as in oracle/icp_ref.c -- results
+  // are bit-identical to the oracle.  flags bit 1: float32 terms accumulated in float64 (order-independent,
+  // ~1e-4 closer to exact arithmetic, a few per cent faster; deviates from the oracle by up to ~2e-3 m on
+  // ill-conditioned scans because the float32-sequential sums themselves are that noisy).
+  const bool seq = (prm.flags & 2) == 0;
   float4 *seq_ws = seq ? b.seq_ws + (size_t)slot * b.ns_max : nullptr;
 
   for (int p = blockIdx.x; p < b.P; p += gridDim.x) {
@@ -498,21 +502,39 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         } else if (prm.outlier_max_dist > 0.f) {
           stop_d2 = out_d2;
         }
-        for (int i = tid; i < ns; i += nthr) {
-          if (qstate[i] & 1) continue;
-          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-          NNResult r;
-          r.pos = match[i] == 0xffff ? -1 : (int)match[i];
-          r.d2 = r.pos >= 0 ? dist[i] : INFINITY;
-          r.tie = 1;  // the candidate came from an earlier pass: re-check ties over the final block
-          const int exact = nn_search(g, q.x, q.y, max_d2, stop_d2, 1, r);
-          if (exact) {
-            const bool fin = r.pos >= 0 && r.d2 <= max_d2;  // == the finiteness found in pass B
-            dist[i] = fin ? r.d2 : INFINITY;
-            match[i] = prev[i] = fin ? (uint16_t)r.pos : (uint16_t)0xffff;
-          } else {
-            dist[i] = ICP_PRUNED;  // finite, farther than the quantile bound: weight 0
-            match[i] = 0xffff;
+        // the unsettled points are few (the scan's outliers) and their searches long: every warp takes the
+        // unsettled points of its 32 lanes one after the other and searches for each with all 32 lanes
+        for (int i0 = tid & ~31; i0 < ns; i0 += nthr) {
+          const int i = i0 + (tid & 31);
+          const bool mine = i < ns && !(qstate[i] & 1);
+          float2 q = make_float2(0.f, 0.f);
+          int cand = -1;
+          float cand_d2 = INFINITY;
+          if (mine) {
+            q = apply_T(Ti, reading[i].x, reading[i].y);
+            cand = match[i] == 0xffff ? -1 : (int)match[i];
+            cand_d2 = cand >= 0 ? dist[i] : INFINITY;
+          }
+          unsigned todo = __ballot_sync(0xffffffffu, mine);
+          while (todo) {
+            const int L = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float qx = __shfl_sync(0xffffffffu, q.x, L), qy = __shfl_sync(0xffffffffu, q.y, L);
+            NNResult r;
+            r.pos = __shfl_sync(0xffffffffu, cand, L);
+            r.d2 = __shfl_sync(0xffffffffu, cand_d2, L);
+            r.tie = 1;  // pass A did not resolve ties; a block scan below replaces this flag with what it finds
+            const int exact = nn_search_warp(g, qx, qy, max_d2, stop_d2, 1, r);
+            if ((tid & 31) == L) {
+              if (exact) {
+                const bool fin = r.pos >= 0 && r.d2 <= max_d2;  // == the finiteness found in pass B
+                dist[i] = fin ? r.d2 : INFINITY;
+                match[i] = prev[i] = fin ? (uint16_t)r.pos : (uint16_t)0xffff;
+              } else {
+                dist[i] = ICP_PRUNED;  // finite, farther than the quantile bound: weight 0
+                match[i] = 0xffff;
+              }
+            }
           }
         }
       }
@@ -839,9 +861,15 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
                                   : (const void *)icp_kernel<512, 1>;
   // the attribute / occupancy queries are cached in the context per (variant, smem): the front end calls this per
   // copy chunk
-  if (smem > ctx->icp_attr_smem[variant]) {
-    SFE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->icp_attr_smem[variant] = smem;
+  {  // the attribute belongs to (function, device), not to a context: only ever raise it, process-wide
+    static std::mutex mu;
+    static size_t attr[64][4] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = attr[ctx->device & 63][variant];
+    if (smem > cur) {
+      SFE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cur = smem;
+    }
   }
   int c_per_sm = 0;
   for (const auto &e : ctx->icp_occ)
@@ -859,7 +887,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   int slots = grid;
   if (per_sm == 1 && P > grid) b.slot_by_smid = 1, slots = ICP_SM_SLOTS, grid = P;  // one CTA per problem
   const size_t orig_bytes = ((size_t)slots * b.nt_max * sizeof(uint16_t) + 15) & ~size_t(15);
-  const size_t seq_bytes = (prm->flags & 2) ? (size_t)slots * b.ns_max * sizeof(float4) : 0;
+  const size_t seq_bytes = (prm->flags & 2) ? 0 : (size_t)slots * b.ns_max * sizeof(float4);
   int rc = ensure(ctx, ctx->scratch[SCR_ICP], orig_bytes + seq_bytes);
   if (rc != SFE_OK) return rc;
   b.orig_ws = (uint16_t *)ctx->scratch[SCR_ICP].ptr;

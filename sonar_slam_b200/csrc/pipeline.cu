@@ -75,10 +75,13 @@ __global__ void fill_offsets_kernel(int32_t *off, int n, int stride) {
 // i-window .. i-1, each moved into frame (i-1)'s coordinates with Keyframe.transform_points
 // (slam_objects.py:178-198: float32 points @ R^T + t), concatenated oldest first.  rel[i][w] is the
 // float32 transform of window slot w (frame i-window+w), rel[i][window] the ICP guess.  One CTA per frame.
+// Frames of the PREVIOUS call kept on the device (sfe_frontend_set_carry): `carry_n` clouds in carry_xy / carry_cnt
+// precede frame 0 of this batch, so virtual frame u = carry_n + (batch index).
 __global__ void __launch_bounds__(256)
     assemble_targets_kernel(const float *__restrict__ clouds, const int32_t *__restrict__ counts, int cap,
                             const float *__restrict__ rel, int f0, int F, int window, float *__restrict__ tgt,
-                            int32_t *__restrict__ tgt_count, int tgt_cap, float *__restrict__ guess) {
+                            int32_t *__restrict__ tgt_count, int tgt_cap, float *__restrict__ guess,
+                            const float *__restrict__ carry_xy, const int32_t *__restrict__ carry_cnt, int carry_n) {
   const int i = f0 + blockIdx.x;  // frames [f0, F) of the batch
   if (i >= F) return;
   const float *myrel = rel + (size_t)i * (window + 1) * 9;
@@ -86,12 +89,13 @@ __global__ void __launch_bounds__(256)
   float *out = tgt + 2 * (size_t)i * tgt_cap;
   int base = 0;
   for (int w = 0; w < window; ++w) {
-    const int k = i - window + w;
-    if (k < 0) continue;
+    const int u = i + carry_n - window + w;  // virtual index of the window frame
+    if (u < 0) continue;
     const float *T = myrel + w * 9;
     const float t0 = T[0], t1 = T[1], t2 = T[2], t3 = T[3], t4 = T[4], t5 = T[5];
-    const int n = min(counts[k], cap);
-    const float *src = clouds + 2 * (size_t)k * cap;
+    const bool carried = u < carry_n;
+    const int n = min(carried ? carry_cnt[u] : counts[u - carry_n], cap);
+    const float *src = carried ? carry_xy + 2 * (size_t)u * cap : clouds + 2 * (size_t)(u - carry_n) * cap;
     for (int j = threadIdx.x; j < n && base + j < tgt_cap; j += blockDim.x) {
       const float x = src[2 * j], y = src[2 * j + 1];
       // numpy's float32 `points.dot(R.T) + t` (slam_objects.py:196): fma(y, r01, x * r00) + tx -- the same
@@ -129,6 +133,11 @@ struct sfe_frontend {
   int rel_turn;
   float *guess, *T;
   int32_t *iters, *inliers, *status;
+  // continuation across calls: the last `window` clouds (+ host poses) of the previous call
+  int carry_on, carry_n;
+  float *carry_xy;       // [window][cap][2]
+  int32_t *carry_cnt;    // [window]
+  double *carry_poses;   // host [window][3]
   cudaStream_t copy_stream;
   cudaEvent_t ev_copy[2], ev_done;
   // optional per-stage timing (CUDA events on the launch stream)
@@ -228,6 +237,9 @@ int sfe_frontend_create(sfe_ctx *ctx, const sfe_maps *maps, const sfe_frontend_p
       sfe_frontend_destroy(fe);
       return SFE_ERR_CUDA;
     }
+  FE_ALLOC(fe->carry_xy, (size_t)params->window * cap * 2 * 4);
+  FE_ALLOC(fe->carry_cnt, (size_t)params->window * 4);
+  fe->carry_poses = new double[3 * (size_t)params->window]();
   FE_ALLOC(fe->guess, F * 9 * 4);
   FE_ALLOC(fe->T, F * 9 * 4);
   FE_ALLOC(fe->iters, F * 4);
@@ -256,9 +268,10 @@ void sfe_frontend_destroy(sfe_frontend *fe) {
   cudaStreamSynchronize(fe->ctx->stream);
   void *bufs[] = {fe->frames, fe->bits, fe->ij, fe->xy_a, fe->xy_b, fe->idx, fe->cnt_a, fe->cnt_b, fe->cnt_c,
                   fe->off_pts, fe->off_tgt, fe->tgt_a, fe->tgt_b, fe->tgt_idx, fe->tcnt_a, fe->tcnt_b, fe->rel,
-                  fe->guess, fe->T, fe->iters, fe->inliers, fe->status};
+                  fe->guess, fe->T, fe->iters, fe->inliers, fe->status, fe->carry_xy, fe->carry_cnt};
   for (void *b : bufs)
     if (b) cudaFree(b);
+  delete[] fe->carry_poses;
   for (int k = 0; k < 2; ++k) {
     if (fe->rel_host[k]) cudaFreeHost(fe->rel_host[k]);
     if (fe->ev_rel[k]) cudaEventDestroy(fe->ev_rel[k]);
@@ -275,23 +288,27 @@ void sfe_frontend_destroy(sfe_frontend *fe) {
   delete fe;
 }
 
-// window transforms + guesses from the odometry poses (host, double), uploaded as float32
+// window transforms + guesses from the odometry poses (host, double), uploaded as float32.  With carried frames the
+// pose sequence is (carried poses ++ this batch's poses): frame i of the batch is virtual frame v = carry_n + i, its
+// reference is virtual frame v - 1 and its window the virtual frames v - window .. v - 1.
 static int fe_upload_poses(sfe_frontend *fe, const double *poses, int n) {
-  const int W = fe->p.window;
+  const int W = fe->p.window, C = fe->carry_n;
   const int turn = fe->rel_turn ^= 1;
   SFE_CUDA(cudaEventSynchronize(fe->ev_rel[turn]));  // the copy that last used this staging buffer (two calls ago)
   float *stage = fe->rel_host[turn];
+  auto pose_of = [&](int v) { return v < C ? fe->carry_poses + 3 * (size_t)v : poses + 3 * (size_t)(v - C); };
   for (int i = 0; i < n; ++i) {
     float *r = stage + (size_t)i * (W + 1) * 9;
+    const int v = C + i;
     for (int w = 0; w < W; ++w) {
-      const int k = i - W + w;
-      if (k >= 0 && i > 0)
-        pose_between(poses + 3 * (size_t)(i - 1), poses + 3 * (size_t)k, r + w * 9);
+      const int u = v - W + w;
+      if (u >= 0 && v > 0)
+        pose_between(pose_of(v - 1), pose_of(u), r + w * 9);
       else
         for (int q = 0; q < 9; ++q) r[w * 9 + q] = (q % 4 == 0) ? 1.f : 0.f;
     }
-    if (i > 0)
-      pose_between(poses + 3 * (size_t)(i - 1), poses + 3 * (size_t)i, r + W * 9);
+    if (v > 0)
+      pose_between(pose_of(v - 1), pose_of(v), r + W * 9);
     else
       for (int q = 0; q < 9; ++q) r[W * 9 + q] = (q % 4 == 0) ? 1.f : 0.f;
   }
@@ -375,7 +392,8 @@ static int fe_match(sfe_frontend *fe, int f0, int n) {
   const float *cloud = fe_cloud(fe, &cnt);
   fe_tic(fe, SFE_FE_SUBMAP);
   assemble_targets_kernel<<<n, 256, 0, ctx->stream>>>(cloud, cnt, cap, fe->rel, f0, f0 + n, p.window, fe->tgt_a,
-                                                      fe->tcnt_a, tcap, fe->guess);
+                                                      fe->tcnt_a, tcap, fe->guess, fe->carry_xy, fe->carry_cnt,
+                                                      fe->carry_n);
   SFE_CUDA(cudaGetLastError());
   ctx->launches++;
   const float *tgt = fe->tgt_a;
@@ -408,6 +426,43 @@ static int fe_match(sfe_frontend *fe, int f0, int n) {
                  ns_small, nt_small);
   fe_toc(fe);
   return rc;
+}
+
+// After a batch: the carried window becomes the last `window` frames of (carried ++ batch), stream-ordered after
+// the batch's matching (which still reads the old carried clouds).  Slots move towards the front, in ascending
+// order, so no frame is overwritten before it has been moved.
+static int fe_update_carry(sfe_frontend *fe, const double *poses, int n) {
+  if (!fe->carry_on) return SFE_OK;
+  const int W = fe->p.window, C = fe->carry_n, total = C + n, keep = total < W ? total : W;
+  const size_t cap = fe->p.cap_points, cbytes = cap * 2 * sizeof(float);
+  const int32_t *cnt;
+  const float *cloud = fe_cloud(fe, &cnt);
+  for (int j = 0; j < keep; ++j) {
+    const int v = total - keep + j;
+    if (v < C) {
+      if (v != j) {
+        SFE_CUDA(cudaMemcpyAsync(fe->carry_xy + (size_t)j * cap * 2, fe->carry_xy + (size_t)v * cap * 2, cbytes,
+                                 cudaMemcpyDeviceToDevice, fe->ctx->stream));
+        SFE_CUDA(cudaMemcpyAsync(fe->carry_cnt + j, fe->carry_cnt + v, 4, cudaMemcpyDeviceToDevice, fe->ctx->stream));
+        memcpy(fe->carry_poses + 3 * (size_t)j, fe->carry_poses + 3 * (size_t)v, 3 * sizeof(double));
+      }
+    } else {
+      const size_t b = (size_t)(v - C);
+      SFE_CUDA(cudaMemcpyAsync(fe->carry_xy + (size_t)j * cap * 2, cloud + b * cap * 2, cbytes, cudaMemcpyDeviceToDevice,
+                               fe->ctx->stream));
+      SFE_CUDA(cudaMemcpyAsync(fe->carry_cnt + j, cnt + b, 4, cudaMemcpyDeviceToDevice, fe->ctx->stream));
+      memcpy(fe->carry_poses + 3 * (size_t)j, poses + 3 * b, 3 * sizeof(double));
+    }
+  }
+  fe->carry_n = keep;
+  return SFE_OK;
+}
+
+int sfe_frontend_set_carry(sfe_frontend *fe, int enable) {
+  SFE_REQUIRE(fe != nullptr, "sfe_frontend_set_carry: null handle");
+  fe->carry_on = enable != 0;
+  if (!fe->carry_on) fe->carry_n = 0;
+  return SFE_OK;
 }
 
 int sfe_frontend_set_timing(sfe_frontend *fe, int enable) {
@@ -449,7 +504,9 @@ int sfe_frontend_run_dev(sfe_frontend *fe, const uint8_t *frames_dev, const doub
   if (rc != SFE_OK) return rc;
   rc = fe_features(fe, frames_dev, 0, n_frames);
   if (rc != SFE_OK) return rc;
-  return fe_match(fe, 0, n_frames);
+  rc = fe_match(fe, 0, n_frames);
+  if (rc != SFE_OK) return rc;
+  return fe_update_carry(fe, poses_host, n_frames);
 }
 
 int sfe_frontend_results_dev(const sfe_frontend *fe, const float **T, const int32_t **iters, const int32_t **inliers,
@@ -495,7 +552,8 @@ int sfe_frontend_run_host(sfe_frontend *fe, const uint8_t *frames_host, const do
     rc = fe_match(fe, f0, n);  // its window only reaches back into chunks already processed
     if (rc != SFE_OK) return rc;
   }
-  int rc = SFE_OK;
+  int rc = fe_update_carry(fe, poses_host, n_frames);
+  if (rc != SFE_OK) return rc;
   SFE_CUDA(cudaMemcpyAsync(T_host, fe->T, sizeof(float) * 9 * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
   SFE_CUDA(cudaMemcpyAsync(iters_host, fe->iters, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));
   SFE_CUDA(cudaMemcpyAsync(inliers_host, fe->inliers, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost, ctx->stream));

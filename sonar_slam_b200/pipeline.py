@@ -67,6 +67,11 @@ class FrontEnd:
         d["cloud_stride"] = stride.value
         return d
 
+    def set_carry(self, enable=True):
+        """Continue the frame sequence across calls: the last `window` clouds and poses stay on the device and serve
+        as the window of the next call's first frames (sfe_frontend_set_carry).  False: every call starts cold."""
+        _lib.check(self.lib.sfe_frontend_set_carry(self.handle, 1 if enable else 0), "sfe_frontend_set_carry")
+
     STAGES = ("cfar", "cart_points", "downsample", "remove_outlier", "submap", "icp")
 
     def set_timing(self, enable=True):

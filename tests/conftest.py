@@ -25,3 +25,35 @@ def gpu_ctx():
     assert torch.cuda.is_available(), "GPU test selected but no CUDA device is visible"
     from sonar_slam_b200 import ops
     return ops.context(0)
+
+
+SHIPPED_ICP_YAML = """matcher:
+  KDTreeMatcher:
+    knn: 1
+    epsilon: 0
+    maxDist: 10.0
+outlierFilters:
+  - MaxDistOutlierFilter:
+      maxDist: 3.0
+  - TrimmedDistOutlierFilter:
+      ratio: 0.8
+errorMinimizer:
+  PointToPointErrorMinimizer
+transformationCheckers:
+  - CounterTransformationChecker:
+      maxIterationCount: 40
+  - DifferentialTransformationChecker:
+      minDiffRotErr: 0.01
+      minDiffTransErr: 0.1
+      smoothLength: 4
+inspector:
+  NullInspector
+"""
+
+
+@pytest.fixture
+def icp_yaml(tmp_path):
+    """The chain bruce_slam/config/icp.yaml ships (icp.yaml:5-28), as a file ICP.loadFromYaml can read."""
+    p = tmp_path / "icp.yaml"
+    p.write_text(SHIPPED_ICP_YAML)
+    return str(p)

@@ -99,3 +99,46 @@ def test_slam_scan_matching_surface(gpu_ctx, tmp_path):
     assert np.array_equal(got, want_pts)
     pts_k, keys = slam.get_points([0, 1, 2], 2, return_keys=True)
     assert np.array_equal(pts_k, want_pts) and set(np.unique(keys)) <= {0.0, 1.0, 2.0}
+
+
+def test_fov_prefilter_equals_reference_lines(gpu_ctx, golden_dir):
+    """Row N3: SLAM.select_targets_in_fov (sfe_fov_select_host) against the fixture produced by exec'ing the
+    reference's own lines slam.py:876-899, and the device entry point against the numpy restatement on a large
+    random cloud (integer/index work: exact)."""
+    import torch
+    from oracle import fov_ref
+    from sonar_slam_b200 import _lib
+    from sonar_slam_b200.bruce_slam.slam import SLAM, Pose2
+    g = np.load(f"{golden_dir}/fov_select.npz")
+    slam = SLAM()
+    slam.oculus.max_range, slam.oculus.horizontal_aperture = float(g["max_range"]), float(g["horizontal_aperture"])
+
+    class KF:
+        def __init__(self, pose, cov):
+            self.pose, self.cov = pose, cov
+
+    slam.keyframes = {int(k): KF(Pose2(*p), c) for k, p, c in zip(g["source_frames"], g["poses"], g["covs"])}
+    pts, keys, sel = slam.select_targets_in_fov(g["target_points"], g["target_keys"], [int(k) for k in g["source_frames"]])
+    assert np.array_equal(sel, g["sel"])
+    assert np.array_equal(pts, g["kept_points"]) and np.array_equal(keys, g["kept_keys"])
+    # no source frames -> nothing selected; empty cloud -> empty
+    assert slam.select_targets_in_fov(g["target_points"], None, [])[2].sum() == 0
+    assert len(slam.select_targets_in_fov(np.zeros((0, 2), np.float32), None, [17])[0]) == 0
+    # device flavour, 200 k points, 5 keyframes
+    rng = np.random.default_rng(4)
+    big = rng.uniform(-60, 60, (200000, 2)).astype(np.float32)
+    T = [Pose2(*(rng.uniform(-1, 1, 3) * [20, 20, 3.1])).inverse().matrix().astype(np.float32) for _ in range(5)]
+    rb, bb = rng.uniform(25, 40, 5), rng.uniform(0.9, 1.6, 5)
+    want = fov_ref.fov_select(big, T, rb, bb)
+    rows = np.array([[t[0, 0], t[0, 1], t[1, 0], t[1, 1], t[0, 2], t[1, 2]] for t in T], np.float32)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pd, Td, rd, bd = d(big), d(rows), d(rb), d(bb)
+    out = torch.empty(len(big), dtype=torch.uint8, device="cuda")
+    ctx = _lib.default_context()
+    _lib.check(ctx.lib.sfe_fov_select_dev(ctx.handle, pd.data_ptr(), len(big), Td.data_ptr(), rd.data_ptr(),
+                                          bd.data_ptr(), 5, out.data_ptr()), "sfe_fov_select_dev")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(bool)
+    # float32 atan2 of numpy (SVML / libm) and of CUDA may differ by an ulp: only points within 4 ulp of a bound may differ
+    diff = np.flatnonzero(got != want)
+    assert len(diff) <= 2, len(diff)

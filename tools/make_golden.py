@@ -309,5 +309,50 @@ def main():
     print("golden fixtures written to", out)
 
 
+def fov_fixture():
+    """tests/golden/fov_select.npz: the reference's own lines slam.py:876-899 (field-of-view pre-filter of the
+    loop-closure targets), exec'ed verbatim on seeded inputs.  The lines sit inside a long method, so they are read
+    from the reference file by number (and checked to be the expected statements) rather than called."""
+    import textwrap
+    from sonar_slam_b200 import synth
+    _install_reference()
+    slam_objects = importlib.import_module("bruce_slam.slam_objects")
+    gtsam = sys.modules["gtsam"]
+    with open(os.path.join(REF_SRC, "bruce_slam", "slam.py")) as f:
+        lines = f.read().split("\n")
+    block = lines[875:899]  # 1-based 876 .. 899
+    assert block[0].strip().startswith("# Loop over the source frames") or "sel = np.zeros" in "".join(block[:4]), block[0]
+    assert block[-1].strip() == "target_keys = target_keys[sel]", block[-1]
+    code = textwrap.dedent("\n".join(block))
+    rng = np.random.default_rng(21)
+    _, tgt, _ = synth.make_icp_pair(3, n_source=100, n_target=6000, extent=80.0)
+    target_points = (tgt + rng.normal(0, 0.01, tgt.shape)).astype(np.float32)
+    target_keys = rng.integers(0, 40, (len(target_points), 1)).astype(np.float32)
+    kfs = {}
+    poses, covs = [], []
+    for k in (17, 16, 15):
+        pose = gtsam.Pose2(*(rng.uniform(-1, 1, 3) * [12.0, 12.0, 1.5]))
+        A = rng.normal(0, 0.3, (3, 3))
+        cov = A @ A.T * np.array([1.0, 1.0, 0.01])[:, None] * np.array([1.0, 1.0, 0.01])[None, :] + np.diag([0.05, 0.05, 1e-4])
+        kfs[k] = types.SimpleNamespace(pose=pose, cov=cov)
+        poses.append([pose.x(), pose.y(), pose.theta()])
+        covs.append(cov)
+    oculus = types.SimpleNamespace(max_range=30.0, horizontal_aperture=np.radians(130.0))
+    ns = dict(np=np, Keyframe=slam_objects.Keyframe, source_frames=range(17, 14, -1),
+              self=types.SimpleNamespace(keyframes=kfs, oculus=oculus),
+              target_points=target_points.copy(), target_keys=target_keys.copy())
+    exec(code, ns)  # noqa: S102 -- the reference's own statements
+    out = os.path.join(REPO, "tests", "golden", "fov_select.npz")
+    np.savez_compressed(out, target_points=target_points, target_keys=target_keys, poses=np.array(poses),
+                        covs=np.array(covs), source_frames=np.array([17, 16, 15]), sel=ns["sel"],
+                        kept_points=ns["target_points"], kept_keys=ns["target_keys"],
+                        max_range=np.float64(30.0), horizontal_aperture=np.float64(np.radians(130.0)))
+    print("fov_select:", len(target_points), "targets ->", int(ns["sel"].sum()), "kept; written to", out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-fov" in sys.argv:
+        fov_fixture()
+    else:
+        main()
+        fov_fixture()
