@@ -350,7 +350,7 @@ def run_ours(args):
     prm20 = _lib.IcpParams(smooth_length=0, max_iterations=20)
     try:
         if rank == 0:
-            P3 = 8 * ctx.sm_count
+            P3 = 8 * torch.cuda.get_device_properties(local).multi_processor_count
             s3, t3, g3 = make_pair_backlog(P3, f"cuda:{local}", n_scenes=16)
             cfg3 = {"pairs": P3, "source_points": 2000, "target_points": 20000, "waves": 8}
             for name, prm in (("fixed20", prm20), ("checkers", _lib.IcpParams())):

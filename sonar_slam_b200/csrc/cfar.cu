@@ -502,10 +502,9 @@ __global__ void __launch_bounds__(CF_W, 5)
 //     (((x + k) | x) & 0x80808080, k = (128 - g_min) * 0x01010101); a thread whose word qualifies parks
 //     (cells, statistic) in its own shared-memory slot of that row with predicated stores and sets a bit in a
 //     16-bit row mask -- the 16-row block is branch-free;
-//   * after the block every thread walks ITS OWN row mask and decides the parked cells against the table M[S]
-//     (atomicOr into a zero-initialised bit tile / byte stores into a mask tile).  The divergence is per lane, not
-//     per row: an echo that crosses a warp's 128 beams on 60 different rows costs each lane its own one or two
-//     rows, not the warp 60 excursions.
+//   * after the block each warp compacts its parked (lane, row) pairs into a queue and decides them 32 at a time
+//     against the table M[S] (atomicOr into a zero-initialised bit tile / byte stores into a mask tile): the
+//     cost follows the NUMBER of candidates, not how they are spread over rows and lanes.
 // ~3.5 instructions per cell instead of ~9 for the table kernel, all-integer, exact: identical to the table
 // kernel by construction (the gate test is a necessary condition; the decision is the same table compare).
 // A strip is 512 beams (128 threads x 4); 16-row chunks arrive by TMA as two [16 x 256] boxes per stage.  Block b
@@ -523,13 +522,14 @@ struct CfarStepG {
 };
 
 // shared-memory layout of cfar_u8_gate4_kernel (dynamic): tile [CG_NS][2][16][256] | obits [2][16][16] |
-// full_bar [CG_NS] | parked statistic [16][128] uint2 | parked cells [16][128] u32 | lut [lut_n padded to 8] |
-// omask [2][16][512] (MASK only)
+// full_bar [CG_NS] | parked statistic [16][128] uint2 | parked cells [16][128] u32 | candidate queues [4][512] u16 |
+// lut [lut_n padded to 8] | omask [2][16][512] (MASK only)
 constexpr size_t CG_OFF_OBITS = (size_t)CG_NS * CF_CH * CG_W;
 constexpr size_t CG_OFF_BAR = CG_OFF_OBITS + sizeof(uint32_t) * 2 * CF_CH * (CG_W / 32);
 constexpr size_t CG_OFF_RECS = CG_OFF_BAR + 64;
 constexpr size_t CG_OFF_RECX = CG_OFF_RECS + sizeof(uint2) * CF_CH * CF_W;
-constexpr size_t CG_OFF_LUT = CG_OFF_RECX + sizeof(uint32_t) * CF_CH * CF_W;
+constexpr size_t CG_OFF_WQ = CG_OFF_RECX + sizeof(uint32_t) * CF_CH * CF_W;  // per-warp candidate queues [4][512] u16
+constexpr size_t CG_OFF_LUT = CG_OFF_WQ + sizeof(uint16_t) * (CF_W / 32) * 32 * CF_CH;
 __host__ __device__ __forceinline__ size_t cg_off_omask(int lut_n) {
   return CG_OFF_LUT + ((sizeof(uint16_t) * (size_t)((lut_n + 7) / 8 * 8) + 15) & ~size_t(15));
 }
@@ -589,27 +589,54 @@ __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][
   SFE_STEP(0) SFE_STEP(1) SFE_STEP(2) SFE_STEP(3) SFE_STEP(4) SFE_STEP(5) SFE_STEP(6) SFE_STEP(7)
   SFE_STEP(8) SFE_STEP(9) SFE_STEP(10) SFE_STEP(11) SFE_STEP(12) SFE_STEP(13) SFE_STEP(14) SFE_STEP(15)
 #undef SFE_STEP
-  // ---- the parked candidates of this thread: the reference's compare, via the table (own slots: no barrier)
-  uint32_t hit = s.hit;
-  while (hit) {
-    const int i = __ffs(hit) - 1;
-    hit &= hit - 1;
-    const int r = r0 + i;
-    if (EDGE && !(r >= CF_HALF && r < p.R - CF_HALF)) continue;  // border rows stay 0
-    const uint2 sv = rec_s[i][tid];
-    const uint32_t xc4 = rec_x[i][tid];
-    uint32_t set = 0;
-#pragma unroll
-    for (int k = 0; k < CG_BEAMS; ++k) {
-      const int x = (int)((xc4 >> (8 * k)) & 255u);
-      const int S = (int)(((k < 2 ? sv.x : sv.y) >> (16 * (k & 1))) & 0xffffu);
-      if (k < nvalid && x >= (int)lut[S]) set |= 1u << k;
+  // ---- the parked candidates: the reference's compare, via the table.  Echoes make candidates a few per cent of
+  //      the cells and put them in runs (a wall crosses a lane on two or three consecutive rows), so a lane
+  //      walking its own list would keep its warp for as many trips as the unluckiest lane has rows.  Instead the
+  //      warp compacts its (lane, row) pairs into a small queue (prefix sum of the per-lane counts, each lane
+  //      appends its own rows) and then decides them 32 at a time -- every trip is full.
+  {
+    const int lane = tid & 31, wbase = tid & ~31;
+    uint16_t *wq = reinterpret_cast<uint16_t *>(cg_smem + CG_OFF_WQ) + (tid >> 5) * (32 * CF_CH);
+    uint32_t hit = s.hit;
+    if (EDGE) {  // border rows stay 0: keep only rows r0 + i in [HALF, R - HALF)
+      const int lo = max(CF_HALF - r0, 0), hi = min(p.R - CF_HALF - r0, CF_CH);
+      hit &= hi > lo ? ((1u << hi) - (1u << lo)) : 0u;
     }
-    if (set) {
-      if (BITS) atomicOr(&obits[ob][i][tid >> 3], set << ((tid & 7) * CG_BEAMS));
-      if (MASK)  // bytes 0/1 of the four beams: spread the 4 bits to 4 bytes
-        *reinterpret_cast<uint32_t *>(&omask[ob][i][CG_BEAMS * tid]) =
-            (set & 1u) | ((set & 2u) << 7) | ((set & 4u) << 14) | ((set & 8u) << 21);
+    const int cnt = __popc(hit);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (tot) {  // (warp-uniform)
+      int pos = incl - cnt;
+      while (hit) {
+        const int i = __ffs(hit) - 1;
+        hit &= hit - 1;
+        wq[pos++] = (uint16_t)((lane << 4) | i);
+      }
+      __syncwarp();  // queue and parked records (written by other lanes of this warp) are visible
+      for (int e = lane; e < tot; e += 32) {
+        const int code = wq[e], i = code & 15, t = wbase + (code >> 4);
+        const uint2 sv = rec_s[i][t];
+        const uint32_t xc4 = rec_x[i][t];
+        const int nv = min(max(p.B - (col0 + CG_BEAMS * t), 0), CG_BEAMS);
+        uint32_t set = 0;
+#pragma unroll
+        for (int k = 0; k < CG_BEAMS; ++k) {
+          const int x = (int)((xc4 >> (8 * k)) & 255u);
+          const int S = (int)(((k < 2 ? sv.x : sv.y) >> (16 * (k & 1))) & 0xffffu);
+          if (k < nv && x >= (int)lut[S]) set |= 1u << k;
+        }
+        if (set) {
+          if (BITS) atomicOr(&obits[ob][i][t >> 3], set << ((t & 7) * CG_BEAMS));
+          if (MASK)  // bytes 0/1 of the four beams: spread the 4 bits to 4 bytes
+            *reinterpret_cast<uint32_t *>(&omask[ob][i][CG_BEAMS * t]) =
+                (set & 1u) | ((set & 2u) << 7) | ((set & 4u) << 14) | ((set & 8u) << 21);
+        }
+      }
     }
   }
   __syncthreads();  // every thread has read tile[st]; the block's detections are in obits[ob] / omask[ob]

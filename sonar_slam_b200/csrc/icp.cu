@@ -212,19 +212,23 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
   return __uint_as_float(prefix);
 }
 
-// exact sequential float32 sum of n values p[0], p[stride], ... in index order (the accumulation order of
-// oracle/icp_ref.c; default mode).  The loads of eight terms are issued together; the adds stay in order.
-__device__ __forceinline__ float seq_sum_f32(const float *p, int n, int stride) {
+// Exact SEQUENTIAL float32 sum of n values p[0], p[stride], ... in index order (the accumulation order of
+// oracle/icp_ref.c; default mode), computed by one warp: the 32 lanes fetch 32 consecutive terms with one
+// coalesced request (the next batch is already in flight while this one is added), and the terms are then added
+// one after the other -- a shuffle hands term j to every lane, so all lanes carry the same running sum.  The
+// dependent chain is the float add alone (~4 cycles per term); lanes beyond n contribute +0, which leaves a sum
+// unchanged bit for bit.  All 32 lanes of the warp must call this.
+__device__ __forceinline__ float seq_sum_f32_warp(const float *p, int n, int stride) {
+  const int lane = threadIdx.x & 31;
   float s = 0.f;
-  int i = 0;
-  for (; i + 8 <= n; i += 8) {
-    float v[8];
+  float cur = lane < n ? p[(size_t)lane * stride] : 0.f;
+  for (int base = 0; base < n; base += 32) {
+    const int nx = base + 32 + lane;
+    const float nxt = nx < n ? p[(size_t)nx * stride] : 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = p[(size_t)(i + k) * stride];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, v[k]);
+    for (int j = 0; j < 32; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, cur, j));
+    cur = nxt;
   }
-  for (; i < n; ++i) s = __fadd_rn(s, p[(size_t)i * stride]);
   return s;
 }
 
@@ -306,7 +310,10 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
     {
       float mx, my;
       if (seq) {
-        if (tid < 2) sh.seq[tid] = __fdiv_rn(seq_sum_f32(tgt + tid, nt, 2), (float)nt);
+        if (tid < 64) {  // warps 0 and 1: x and y
+          const float sum = seq_sum_f32_warp(tgt + (tid >> 5), nt, 2);
+          if ((tid & 31) == 0) sh.seq[tid >> 5] = __fdiv_rn(sum, (float)nt);
+        }
         __syncthreads();
         mx = sh.seq[0], my = sh.seq[1];
       } else {
@@ -612,7 +619,10 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         break;
       }
       if (seq) {
-        if (tid < 4) sh.seq[tid] = seq_sum_f32(reinterpret_cast<const float *>(seq_ws) + tid, ns, 4);
+        if (tid < 128) {  // warps 0..3: one component each
+          const float sum = seq_sum_f32_warp(reinterpret_cast<const float *>(seq_ws) + (tid >> 5), ns, 4);
+          if ((tid & 31) == 0) sh.seq[tid >> 5] = sum;
+        }
         __syncthreads();
         mrx = sh.seq[0], mry = sh.seq[1], mfx = sh.seq[2], mfy = sh.seq[3];
         __syncthreads();  // sh.seq and seq_ws are rewritten below
@@ -636,7 +646,10 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
           seq_ws[i] = make_float4(__fmul_rn(qx, px), __fmul_rn(qx, py), __fmul_rn(qy, px), __fmul_rn(qy, py));
         }
         __syncthreads();
-        if (tid < 4) sh.seq[tid] = seq_sum_f32(reinterpret_cast<const float *>(seq_ws) + tid, ns, 4);
+        if (tid < 128) {
+          const float sum = seq_sum_f32_warp(reinterpret_cast<const float *>(seq_ws) + (tid >> 5), ns, 4);
+          if ((tid & 31) == 0) sh.seq[tid >> 5] = sum;
+        }
         __syncthreads();
         t4[0] = (double)sh.seq[0], t4[1] = (double)sh.seq[1], t4[2] = (double)sh.seq[2], t4[3] = (double)sh.seq[3];
       } else {

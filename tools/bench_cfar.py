@@ -7,13 +7,19 @@ import torch
 from sonar_slam_b200 import ops
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+DATA = sys.argv[2] if len(sys.argv) > 2 else "replay"   # replay: bench.py's frames (speckle + echoes); noise: speckle
 TAU = 2.749063720096473
 torch.cuda.set_device(0)
-g = torch.Generator(device="cuda").manual_seed(0)
-imgs = torch.empty((F, 512, 512), dtype=torch.uint8, device="cuda")
-for i in range(0, F, 256):
-    u = torch.rand((min(256, F - i), 512, 512), device="cuda", generator=g).clamp_min(1e-7)
-    imgs[i:i + 256] = torch.clamp(torch.round(18.0 * torch.sqrt(-2.0 * torch.log(u))), 0, 255).to(torch.uint8)
+if DATA == "replay":
+    from sonar_slam_b200 import synth
+    imgs = synth.make_trajectory_frames(F, seed=0, device="cuda")["frames"]
+else:
+    g = torch.Generator(device="cuda").manual_seed(0)
+    imgs = torch.empty((F, 512, 512), dtype=torch.uint8, device="cuda")
+    for i in range(0, F, 256):
+        u = torch.rand((min(256, F - i), 512, 512), device="cuda", generator=g).clamp_min(1e-7)
+        imgs[i:i + 256] = torch.clamp(torch.round(18.0 * torch.sqrt(-2.0 * torch.log(u))), 0, 255).to(torch.uint8)
+print("data:", DATA, "cells >= 66:", float((imgs[:64] >= 66).float().mean()))
 res = {}
 for name, x in (("f32", imgs.float()), ("u8", imgs)):
     for outs in (dict(want_mask=True), dict(want_mask=False, want_bits=True), dict(want_mask=True, want_bits=True)):

@@ -11,9 +11,9 @@ for s in $steps; do
   case $s in
     tests)    timeout 1200 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/${tag}_pytest.log 2>&1; tail -5 gpurun_out/${tag}_pytest.log ;;
     tests_all) timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${tag}_pytest.log 2>&1; tail -15 gpurun_out/${tag}_pytest.log ;;
-    cfar)     SFE_CFAR_U8_KERNEL=lut timeout 300 python tools/bench_cfar.py 4096 u8 > gpurun_out/${tag}_cfar_lut.log 2>&1
-              timeout 300 python tools/bench_cfar.py 4096 > gpurun_out/${tag}_cfar.log 2>&1; cp gpurun_out/bench_cfar.json gpurun_out/${tag}_bench_cfar.json
-              grep -E "u8_SOCA" gpurun_out/${tag}_cfar_lut.log gpurun_out/${tag}_cfar.log ;;
+    cfar)     SFE_CFAR_U8_KERNEL=lut timeout 300 python tools/bench_cfar.py 4096 replay > gpurun_out/${tag}_cfar_lut.log 2>&1
+              timeout 300 python tools/bench_cfar.py 4096 noise > gpurun_out/${tag}_cfar_noise.log 2>&1; timeout 300 python tools/bench_cfar.py 4096 replay > gpurun_out/${tag}_cfar.log 2>&1; cp gpurun_out/bench_cfar.json gpurun_out/${tag}_bench_cfar.json
+              grep -E "u8_SOCA|data:" gpurun_out/${tag}_cfar_lut.log gpurun_out/${tag}_cfar_noise.log gpurun_out/${tag}_cfar.log ;;
     icp)      timeout 600 python tools/icp_scaling.py > gpurun_out/${tag}_icp_scaling.log 2>&1; cat gpurun_out/${tag}_icp_scaling.log ;;
     stages)   timeout 600 python tools/bench_stages.py 4096 1184 > gpurun_out/${tag}_stages.log 2>&1; cat gpurun_out/${tag}_stages.log ;;
     bench)    timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 3000 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err ;;
