@@ -195,9 +195,10 @@ int sfe_cfar_host(sfe_ctx *ctx, const void *img_host, int dtype, int n_frames, i
 // ============================================================================ clouds / match / ICP
 namespace sfe {
 int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
-                   float resolution, float *out_pts, int32_t *out_idx, int32_t *out_count);
+                   float resolution, float *out_pts, int32_t *out_idx, int32_t *out_count, int n_split = 0);
 int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
-                       double radius, int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count);
+                       double radius, int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count,
+                       int n_split = 0);
 int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
             const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
             const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,

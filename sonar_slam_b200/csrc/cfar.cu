@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(CF_W, 5)
 // kernel by construction (the gate test is a necessary condition; the decision is the same table compare).
 // A strip is 512 beams (128 threads x 4); 16-row chunks arrive by TMA as two [16 x 256] boxes per stage.  Block b
 // consumes chunk b (newest cell rn = 16 b + i) and decides cell r = rn - 25, so every block touches ONE tile.
+// The four warps of a CTA only share the tiles: no CTA barrier in the loop (see cfar_block16_g).
 constexpr int CG_BEAMS = 4;
 constexpr int CG_W = CF_W * CG_BEAMS;  // beams per strip
 constexpr int CG_NS = 4;               // input ring depth
@@ -521,11 +522,11 @@ struct CfarStepG {
   uint32_t hit;                        // rows of the current block with a parked candidate word
 };
 
-// shared-memory layout of cfar_u8_gate4_kernel (dynamic): tile [CG_NS][2][16][256] | obits [2][16][16] |
-// full_bar [CG_NS] | parked statistic [16][128] uint2 | parked cells [16][128] u32 | candidate queues [4][512] u16 |
-// lut [lut_n padded to 8] | omask [2][16][512] (MASK only)
+// shared-memory layout of cfar_u8_gate4_kernel (dynamic): tile [CG_NS][2][16][256] | obits [16][16] |
+// full_bar [CG_NS] + stage counters [CG_NS] | parked statistic [16][128] uint2 | parked cells [16][128] u32 | candidate queues [4][512] u16 |
+// lut [lut_n padded to 8] | omask [16][512] (MASK only)
 constexpr size_t CG_OFF_OBITS = (size_t)CG_NS * CF_CH * CG_W;
-constexpr size_t CG_OFF_BAR = CG_OFF_OBITS + sizeof(uint32_t) * 2 * CF_CH * (CG_W / 32);
+constexpr size_t CG_OFF_BAR = CG_OFF_OBITS + sizeof(uint32_t) * CF_CH * (CG_W / 32);
 constexpr size_t CG_OFF_RECS = CG_OFF_BAR + 64;
 constexpr size_t CG_OFF_RECX = CG_OFF_RECS + sizeof(uint2) * CF_CH * CF_W;
 constexpr size_t CG_OFF_WQ = CG_OFF_RECX + sizeof(uint32_t) * CF_CH * CF_W;  // per-warp candidate queues [4][512] u16
@@ -561,17 +562,22 @@ __device__ __forceinline__ void cfar_step_g(CfarStepG &s, const uint32_t xn4, co
   }
 }
 
+// One 16-row block of one WARP (128 beams).  The four warps of a CTA share the TMA tiles and nothing else: each has
+// its own slice of the output tiles, its own parked records and queue, so there is no CTA barrier in the loop --
+// an echo-rich warp does not hold the others up.  A stage of the input ring is refilled by whichever warp is the
+// last to have read it (a shared-memory counter per stage; the reads are ordered before the TMA write by the
+// fences around the counter update).
 template <int ALG, bool MASK, bool BITS, bool EDGE, int Q>
 __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][CF_CH][CG_W / 2],
-                                               uint32_t (*obits)[CF_CH][CG_W / 32], uint8_t (*omask)[CF_CH][CG_W],
-                                               uint64_t *full_bar, const CUtensorMap *in_map,
+                                               uint32_t (*obits)[CG_W / 32], uint8_t (*omask)[CG_W],
+                                               uint64_t *full_bar, int *stage_cnt, const CUtensorMap *in_map,
                                                const uint16_t *__restrict__ lut, const CfarParams &p, const int blk,
                                                const int nchunks, const int tid, const int f, const int col0,
-                                               const uint32_t gate_add, const int nvalid) {
+                                               const uint32_t gate_add) {
   const int r0 = blk * CF_CH - CF_HALF;  // first output row of this block
-  constexpr int ob = Q & 1;
   const int st = blk & (CG_NS - 1);
   const bool has = EDGE ? (blk < nchunks) : true;
+  const int lane = tid & 31, warp = tid >> 5, wbase = tid & ~31;
   uint2(*rec_s)[CF_W] = reinterpret_cast<uint2(*)[CF_W]>(cg_smem + CG_OFF_RECS);
   uint32_t(*rec_x)[CF_W] = reinterpret_cast<uint32_t(*)[CF_W]>(cg_smem + CG_OFF_RECX);
   uint32_t xin[CF_CH];
@@ -589,14 +595,29 @@ __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][
   SFE_STEP(0) SFE_STEP(1) SFE_STEP(2) SFE_STEP(3) SFE_STEP(4) SFE_STEP(5) SFE_STEP(6) SFE_STEP(7)
   SFE_STEP(8) SFE_STEP(9) SFE_STEP(10) SFE_STEP(11) SFE_STEP(12) SFE_STEP(13) SFE_STEP(14) SFE_STEP(15)
 #undef SFE_STEP
+  // ---- this warp is done with tile[st]: the last of the four warps to say so refills the stage
+  if (has) {
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();  // our reads of the tile come before the counter update ...
+      if (atomicAdd(&stage_cnt[st], 1) == CF_W / 32 - 1) {
+        stage_cnt[st] = 0;
+        __threadfence_block();  // ... and everybody's counter update before the refill
+        if (blk + CG_NS < nchunks) {
+          mbar_arrive_expect_tx(&full_bar[st], CF_CH * CG_W);
+          tma_load_3d(&tile[st][0][0][0], in_map, &full_bar[st], col0, (blk + CG_NS) * CF_CH, f);
+          tma_load_3d(&tile[st][1][0][0], in_map, &full_bar[st], col0 + CG_W / 2, (blk + CG_NS) * CF_CH, f);
+        }
+      }
+    }
+  }
   // ---- the parked candidates: the reference's compare, via the table.  Echoes make candidates a few per cent of
   //      the cells and put them in runs (a wall crosses a lane on two or three consecutive rows), so a lane
   //      walking its own list would keep its warp for as many trips as the unluckiest lane has rows.  Instead the
   //      warp compacts its (lane, row) pairs into a small queue (prefix sum of the per-lane counts, each lane
-  //      appends its own rows) and then decides them 32 at a time -- every trip is full.
+  //      appends its own rows) and then decides them 32 at a time.
   {
-    const int lane = tid & 31, wbase = tid & ~31;
-    uint16_t *wq = reinterpret_cast<uint16_t *>(cg_smem + CG_OFF_WQ) + (tid >> 5) * (32 * CF_CH);
+    uint16_t *wq = reinterpret_cast<uint16_t *>(cg_smem + CG_OFF_WQ) + warp * (32 * CF_CH);
     uint32_t hit = s.hit;
     if (EDGE) {  // border rows stay 0: keep only rows r0 + i in [HALF, R - HALF)
       const int lo = max(CF_HALF - r0, 0), hi = min(p.R - CF_HALF - r0, CF_CH);
@@ -631,29 +652,23 @@ __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][
           if (k < nv && x >= (int)lut[S]) set |= 1u << k;
         }
         if (set) {
-          if (BITS) atomicOr(&obits[ob][i][t >> 3], set << ((t & 7) * CG_BEAMS));
+          if (BITS) atomicOr(&obits[i][t >> 3], set << ((t & 7) * CG_BEAMS));
           if (MASK)  // bytes 0/1 of the four beams: spread the 4 bits to 4 bytes
-            *reinterpret_cast<uint32_t *>(&omask[ob][i][CG_BEAMS * t]) =
+            *reinterpret_cast<uint32_t *>(&omask[i][CG_BEAMS * t]) =
                 (set & 1u) | ((set & 2u) << 7) | ((set & 4u) << 14) | ((set & 8u) << 21);
         }
       }
     }
-  }
-  __syncthreads();  // every thread has read tile[st]; the block's detections are in obits[ob] / omask[ob]
-  if (tid == 0 && blk + CG_NS < nchunks) {
-    mbar_arrive_expect_tx(&full_bar[st], CF_CH * CG_W);
-    tma_load_3d(&tile[st][0][0][0], in_map, &full_bar[st], col0, (blk + CG_NS) * CF_CH, f);
-    tma_load_3d(&tile[st][1][0][0], in_map, &full_bar[st], col0 + CG_W / 2, (blk + CG_NS) * CF_CH, f);
+    __syncwarp();  // the warp's slice of the output tiles is complete
   }
   if (EDGE && r0 + CF_CH <= 0) return;  // nothing to write yet (and nothing was set)
-  // hand the 16 rows to global memory and clear them for the block after next (the thread that reads a word is
-  // the one that clears it; the buffer is next written after the NEXT block's barrier)
+  // ---- hand the warp's 16 rows x 128 beams to global memory and clear them for the next block
   if (BITS) {
-    const int i = tid >> 3, wq = (tid & 7) * 2;  // 16 rows x 16 words = 128 x uint2
-    uint2 *src = reinterpret_cast<uint2 *>(&obits[ob][i][wq]);
+    const int i = lane >> 1, wq2 = warp * (CF_W / 32) + (lane & 1) * 2;  // 16 rows x 4 words = 32 x uint2
+    uint2 *src = reinterpret_cast<uint2 *>(&obits[i][wq2]);
     const uint2 v = *src;
     *src = make_uint2(0u, 0u);
-    const int r = r0 + i, w = (col0 >> 5) + wq;
+    const int r = r0 + i, w = (col0 >> 5) + wq2;
     if (r >= 0 && r < p.R) {
       uint32_t *dst = p.bits + ((size_t)f * p.R + r) * p.words_per_row + w;
       if (w + 1 < p.words_per_row && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0) {
@@ -666,16 +681,17 @@ __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][
   }
   if (MASK) {
 #pragma unroll
-    for (int j = 0; j < CF_CH * (CG_W / 16) / CF_W; ++j) {  // 16 rows x 32 uint4 over 128 threads
-      const int idx = tid + j * CF_W, i = idx / (CG_W / 16), sg = idx % (CG_W / 16);
-      uint4 *src = reinterpret_cast<uint4 *>(&omask[ob][i][sg * 16]);
+    for (int j = 0; j < CF_CH * (CG_W / 4 / 16) / 32; ++j) {  // 16 rows x 8 uint4 (this warp's 128 beams) over 32 lanes
+      const int idx = lane + j * 32, i = idx >> 3, sg = idx & 7;
+      uint4 *src = reinterpret_cast<uint4 *>(&omask[i][warp * (CG_W / 4) + sg * 16]);
       const uint4 v = *src;
       *src = make_uint4(0u, 0u, 0u, 0u);
-      const int r = r0 + i, c = col0 + sg * 16;
+      const int r = r0 + i, c = col0 + warp * (CG_W / 4) + sg * 16;
       if (r >= 0 && r < p.R && c < p.B)  // B % 16 == 0 and mask 16-byte aligned (checked by the host)
         *reinterpret_cast<uint4 *>(p.mask + ((size_t)f * p.R + r) * p.B + c) = v;
     }
   }
+  __syncwarp();
 }
 
 template <int ALG, bool MASK, bool BITS>
@@ -683,10 +699,11 @@ __global__ void __launch_bounds__(CF_W, MASK ? 2 : 3)
     cfar_u8_gate4_kernel(const __grid_constant__ CUtensorMap in_map, CfarParams p, const uint16_t *__restrict__ lut_g,
                          const int lut_n, const uint32_t gate_add) {
   uint8_t(*tile)[2][CF_CH][CG_W / 2] = reinterpret_cast<uint8_t(*)[2][CF_CH][CG_W / 2]>(cg_smem);
-  uint32_t(*obits)[CF_CH][CG_W / 32] = reinterpret_cast<uint32_t(*)[CF_CH][CG_W / 32]>(cg_smem + CG_OFF_OBITS);
+  uint32_t(*obits)[CG_W / 32] = reinterpret_cast<uint32_t(*)[CG_W / 32]>(cg_smem + CG_OFF_OBITS);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(cg_smem + CG_OFF_BAR);
+  int *stage_cnt = reinterpret_cast<int *>(cg_smem + CG_OFF_BAR + 8 * CG_NS);
   uint16_t *lut = reinterpret_cast<uint16_t *>(cg_smem + CG_OFF_LUT);
-  uint8_t(*omask)[CF_CH][CG_W] = reinterpret_cast<uint8_t(*)[CF_CH][CG_W]>(cg_smem + cg_off_omask(lut_n));
+  uint8_t(*omask)[CG_W] = reinterpret_cast<uint8_t(*)[CG_W]>(cg_smem + cg_off_omask(lut_n));
 
   const int tid = threadIdx.x;
   const int f = blockIdx.x / p.strips;
@@ -695,7 +712,7 @@ __global__ void __launch_bounds__(CF_W, MASK ? 2 : 3)
   const int nchunks = (R + CF_CH - 1) / CF_CH;
   if (tid == 0) {
     prefetch_tmap(&in_map);
-    for (int st = 0; st < CG_NS; ++st) mbar_init(&full_bar[st], 1);
+    for (int st = 0; st < CG_NS; ++st) mbar_init(&full_bar[st], 1), stage_cnt[st] = 0;
     fence_mbar_init();
     for (int c = 0; c < CG_NS && c < nchunks; ++c) {
       mbar_arrive_expect_tx(&full_bar[c], CF_CH * CG_W);
@@ -705,16 +722,15 @@ __global__ void __launch_bounds__(CF_W, MASK ? 2 : 3)
   }
   for (int i = tid; i * 8 < lut_n; i += CF_W) reinterpret_cast<uint4 *>(lut)[i] = reinterpret_cast<const uint4 *>(lut_g)[i];
   if (BITS)
-    for (int i = tid; i < 2 * CF_CH * (CG_W / 32); i += CF_W) (&obits[0][0][0])[i] = 0u;
+    for (int i = tid; i < CF_CH * (CG_W / 32); i += CF_W) (&obits[0][0])[i] = 0u;
   if (MASK)
-    for (int i = tid; i < 2 * CF_CH * CG_W / 16; i += CF_W) reinterpret_cast<uint4 *>(&omask[0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < CF_CH * CG_W / 16; i += CF_W) reinterpret_cast<uint4 *>(&omask[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 
   CfarStepG s;
 #pragma unroll
   for (int i = 0; i < CF_RING; ++i) s.xr[i] = 0u, s.wl[i] = 0u, s.wh[i] = 0u;
   s.w_lo = 0u, s.w_hi = 0u, s.hit = 0u;
-  const int nvalid = min(max(p.B - (col0 + CG_BEAMS * tid), 0), CG_BEAMS);
   // block b: newest cells rn = 16 b .. 16 b + 15, decides rows rn - 25; the last decided row is R - 1
   const int nblk = (R + CF_HALF + CF_CH - 1) / CF_CH;
   for (int b2 = 0; b2 * 2 < nblk; ++b2) {
@@ -725,7 +741,7 @@ __global__ void __launch_bounds__(CF_W, MASK ? 2 : 3)
         const int r0 = blk * CF_CH - CF_HALF;
         const bool interior = (r0 >= CF_HALF) && (r0 + CF_CH - 1 < R - CF_HALF) && blk < nchunks;
 #define SFE_BLOCK(EDGE_, Q_) \
-  cfar_block16_g<ALG, MASK, BITS, EDGE_, Q_>(s, tile, obits, omask, full_bar, &in_map, lut, p, blk, nchunks, tid, f, col0, gate_add, nvalid)
+  cfar_block16_g<ALG, MASK, BITS, EDGE_, Q_>(s, tile, obits, omask, full_bar, stage_cnt, &in_map, lut, p, blk, nchunks, tid, f, col0, gate_add)
         if (interior) {
           if (q == 0) SFE_BLOCK(false, 0); else SFE_BLOCK(false, 1);
         } else {
@@ -916,7 +932,7 @@ static int launch_u8_gate4(sfe_ctx *ctx, const CUtensorMap &in_map, const CfarPa
                            uint32_t gate_add) {
   const bool m = p.mask != nullptr, b = p.bits != nullptr;
   const int grid = p.F * p.strips;
-  const size_t smem = cg_off_omask(lut_n) + (m ? 2 * CF_CH * CG_W : 0);
+  const size_t smem = cg_off_omask(lut_n) + (m ? CF_CH * CG_W : 0);
 #define SFE_GO(M_, B_)                                                                                              \
   do {                                                                                                              \
     SFE_CUDA(cudaFuncSetAttribute(cfar_u8_gate4_kernel<ALG, M_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \

@@ -35,6 +35,8 @@ struct CloudBatch {
   const int *off;    // [n_clouds + 1] first row of every cloud
   const int *cnt;    // optional [n_clouds]: rows used (else off[c+1]-off[c]); clamped to n_max
   int n_clouds, dim, n_max, n_pad, max_cells;
+  int n_lo, n_hi;    // size class of this launch: only clouds with n_lo < n <= n_hi are processed (others untouched)
+  int n_lay;         // the launch's shared-memory layout / workspace stride is sized for clouds of n_lay points
   float resolution;  // downsample
   double radius;     // remove_outlier
   int min_points;
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
 
   for (int cl = blockIdx.x; cl < b.n_clouds; cl += gridDim.x) {
     const int o = b.off[cl], n = min(b.cnt ? b.cnt[cl] : b.off[cl + 1] - o, b.n_max);
+    if (!(n > b.n_lo && n <= b.n_hi)) continue;  // the other launch's size class (CTA-uniform)
     const float *pts = b.pts + (size_t)o * b.dim;
     __syncthreads();
     if (n == 0) {
@@ -339,14 +342,15 @@ __global__ void __launch_bounds__(CLOUD_THREADS) remove_outlier_kernel(const Clo
   __shared__ float bbox[4];
   __shared__ int scan[36];
   float2 *sorted = reinterpret_cast<float2 *>(smem_raw);
-  uint32_t *cells = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float2) * (size_t)b.n_max);
+  uint32_t *cells = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float2) * (size_t)b.n_lay);
   const int tid = threadIdx.x, nthr = blockDim.x;
-  uint16_t *orig = b.orig_ws + (size_t)blockIdx.x * b.n_max;
+  uint16_t *orig = b.orig_ws + (size_t)blockIdx.x * b.n_lay;
   const double r2 = b.radius * b.radius;
   const float rw = (float)(b.radius * (1.0 + 1e-5) + 1e-6);  // search window, slightly widened
 
   for (int cl = blockIdx.x; cl < b.n_clouds; cl += gridDim.x) {
     const int o = b.off[cl], n = min(b.cnt ? b.cnt[cl] : b.off[cl + 1] - o, b.n_max);
+    if (!(n > b.n_lo && n <= b.n_hi)) continue;  // the other launch's size class (CTA-uniform)
     const float *pts = b.pts + (size_t)o * b.dim;
     __syncthreads();
     if (n == 0) {
@@ -428,32 +432,22 @@ static int next_pow2(int v) {
   return p;
 }
 
-int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
-                   float resolution,
-                   float *out_pts, int32_t *out_idx, int32_t *out_count) {
-  SFE_REQUIRE(ctx, "downsample: null context");
-  SFE_REQUIRE(n_clouds >= 0 && n_max >= 0, "downsample: negative sizes");
-  SFE_REQUIRE(dim == 2 || dim == 3, "downsample: points must have 2 or 3 columns (got %d)", dim);
-  if (n_clouds == 0) return SFE_OK;
-  SFE_REQUIRE(pts && off && out_pts && out_idx && out_count, "downsample: null pointer");
-  SFE_REQUIRE(dim == 2, "downsample: only 2-column clouds are supported (the reference only passes [x, y])");
-  CloudBatch b{};
-  b.pts = pts, b.off = off, b.cnt = cnt, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
-  b.n_pad = next_pow2(b.n_max);
-  b.resolution = resolution;
-  b.out_pts = out_pts, b.out_idx = out_idx, b.out_count = out_count;
-  size_t smem_sort = sizeof(unsigned long long) * (size_t)b.n_pad, smem_acc = sizeof(float) * (size_t)b.n_max + 16;
+// One launch of a size class: layout for clouds of n_lay points, clouds with n_lo < n <= n_hi.
+static int downsample_launch(sfe_ctx *ctx, CloudBatch b, int n_lay, int n_lo, int n_hi) {
+  b.n_lay = n_lay, b.n_lo = n_lo, b.n_hi = n_hi;
+  b.n_pad = next_pow2(n_lay);
+  size_t smem_sort = sizeof(unsigned long long) * (size_t)b.n_pad, smem_acc = sizeof(float) * (size_t)n_lay + 16;
   b.sort_in_smem = smem_sort + smem_acc <= (size_t)ctx->max_smem_optin - 4096;
   size_t smem = (b.sort_in_smem ? smem_sort : 0) + smem_acc;
   {
-    const size_t a16 = (sizeof(uint16_t) * (size_t)b.n_max + 15) & ~size_t(15);
-    const size_t lay_a = a16 + sizeof(uint32_t) * (DS_FAST_CELLS / 2 + 4) + a16 + sizeof(float) * (size_t)b.n_max + 16;
-    const size_t lay_b = 2 * a16 + sizeof(uint32_t) * (DS_WIDE_CELLS / 2 + 4) + a16 + sizeof(float) * (size_t)b.n_max + 16;
+    const size_t a16 = (sizeof(uint16_t) * (size_t)n_lay + 15) & ~size_t(15);
+    const size_t lay_a = a16 + sizeof(uint32_t) * (DS_FAST_CELLS / 2 + 4) + a16 + sizeof(float) * (size_t)n_lay + 16;
+    const size_t lay_b = 2 * a16 + sizeof(uint32_t) * (DS_WIDE_CELLS / 2 + 4) + a16 + sizeof(float) * (size_t)n_lay + 16;
     const size_t fast = lay_a > lay_b ? lay_a : lay_b;
-    if (b.n_max <= 65535 && fast <= (size_t)ctx->max_smem_optin - 4096 && fast > smem) smem = fast;
+    if (n_lay <= 65535 && fast <= (size_t)ctx->max_smem_optin - 4096 && fast > smem) smem = fast;
   }
   if (smem > (size_t)ctx->max_smem_optin - 4096) {
-    set_error("downsample: clouds of %d points are not supported (shared memory)", n_max);
+    set_error("downsample: clouds of %d points are not supported (shared memory)", n_lay);
     return SFE_ERR_UNSUPPORTED;
   }
   b.smem_bytes = (int)smem;
@@ -462,7 +456,7 @@ int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cn
   SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, downsample_kernel, CLOUD_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   int grid = ctx->sm_count * per_sm;
-  if (grid > n_clouds) grid = n_clouds;
+  if (grid > b.n_clouds) grid = b.n_clouds;
   if (!b.sort_in_smem) {
     int rc = ensure(ctx, ctx->scratch[SCR_CLOUD], sizeof(unsigned long long) * (size_t)grid * b.n_pad);
     if (rc != SFE_OK) return rc;
@@ -474,9 +468,60 @@ int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cn
   return SFE_OK;
 }
 
+// n_split > 0 (front end): two launches by cloud size.  The buffers are sized for n_max points per cloud, the
+// clouds of a sonar frame are far smaller, and the kernel's occupancy is set by its shared-memory layout: the first
+// launch is laid out for clouds of up to n_split points (3-4 CTAs per SM instead of 2) and skips larger ones, the
+// second, laid out for n_max, takes only those (normally none: its CTAs read the counts and leave).
+int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
+                   float resolution, float *out_pts, int32_t *out_idx, int32_t *out_count, int n_split) {
+  SFE_REQUIRE(ctx, "downsample: null context");
+  SFE_REQUIRE(n_clouds >= 0 && n_max >= 0, "downsample: negative sizes");
+  SFE_REQUIRE(dim == 2 || dim == 3, "downsample: points must have 2 or 3 columns (got %d)", dim);
+  if (n_clouds == 0) return SFE_OK;
+  SFE_REQUIRE(pts && off && out_pts && out_idx && out_count, "downsample: null pointer");
+  SFE_REQUIRE(dim == 2, "downsample: only 2-column clouds are supported (the reference only passes [x, y])");
+  CloudBatch b{};
+  b.pts = pts, b.off = off, b.cnt = cnt, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
+  b.resolution = resolution;
+  b.out_pts = out_pts, b.out_idx = out_idx, b.out_count = out_count;
+  if (n_split > 0 && n_split < b.n_max) {
+    int rc = downsample_launch(ctx, b, n_split, -1, n_split);
+    if (rc != SFE_OK) return rc;
+    return downsample_launch(ctx, b, b.n_max, n_split, b.n_max);
+  }
+  return downsample_launch(ctx, b, b.n_max, -1, b.n_max);
+}
+
+static int remove_outlier_launch(sfe_ctx *ctx, CloudBatch b, int n_lay, int n_lo, int n_hi) {
+  b.n_lay = n_lay, b.n_lo = n_lo, b.n_hi = n_hi;
+  b.max_cells = 2 * n_lay < 256 ? 256 : (2 * n_lay > GRID_MAX_CELLS ? GRID_MAX_CELLS : 2 * n_lay);
+  const size_t smem = sizeof(float2) * (size_t)n_lay + sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 16;
+  if (smem > (size_t)ctx->max_smem_optin - 4096) {
+    set_error("remove_outlier: clouds of %d points are not supported (shared memory)", n_lay);
+    return SFE_ERR_UNSUPPORTED;
+  }
+  // small clouds: smaller CTAs, more of them per SM (the stages are latency-bound chains; concurrency hides them)
+  const int threads = n_lay <= 1024 ? 256 : CLOUD_THREADS;
+  SFE_CUDA(cudaFuncSetAttribute(remove_outlier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remove_outlier_kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = ctx->sm_count * per_sm;
+  if (grid > b.n_clouds) grid = b.n_clouds;
+  // (each class keeps its own workspace: the launches of one call may overlap on the stream's timeline only in
+  // order, but the strides differ)
+  int rc = ensure(ctx, ctx->scratch[SCR_MISC], (size_t)grid * n_lay * sizeof(uint16_t));
+  if (rc != SFE_OK) return rc;
+  b.orig_ws = (uint16_t *)ctx->scratch[SCR_MISC].ptr;
+  remove_outlier_kernel<<<grid, threads, smem, ctx->stream>>>(b);
+  SFE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SFE_OK;
+}
+
 int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
-                       double radius,
-                       int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count) {
+                       double radius, int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count,
+                       int n_split) {
   SFE_REQUIRE(ctx, "remove_outlier: null context");
   SFE_REQUIRE(n_clouds >= 0 && n_max >= 0, "remove_outlier: negative sizes");
   SFE_REQUIRE(dim == 2 || dim == 3, "remove_outlier: points must have 2 or 3 columns (got %d)", dim);
@@ -487,26 +532,13 @@ int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int
   CloudBatch b{};
   b.pts = pts, b.off = off, b.cnt = cnt, b.n_clouds = n_clouds, b.dim = dim, b.n_max = n_max > 0 ? n_max : 1;
   b.radius = radius, b.min_points = min_points;
-  b.max_cells = 2 * b.n_max < 256 ? 256 : (2 * b.n_max > GRID_MAX_CELLS ? GRID_MAX_CELLS : 2 * b.n_max);
   b.out_pts = out_pts, b.out_idx = out_idx, b.out_count = out_count;
-  const size_t smem = sizeof(float2) * (size_t)b.n_max + sizeof(uint32_t) * (size_t)((b.max_cells + 2) / 2 + 1) + 16;
-  if (smem > (size_t)ctx->max_smem_optin - 4096) {
-    set_error("remove_outlier: clouds of %d points are not supported (shared memory)", n_max);
-    return SFE_ERR_UNSUPPORTED;
+  if (n_split > 0 && n_split < b.n_max) {
+    int rc = remove_outlier_launch(ctx, b, n_split, -1, n_split);
+    if (rc != SFE_OK) return rc;
+    return remove_outlier_launch(ctx, b, b.n_max, n_split, b.n_max);
   }
-  SFE_CUDA(cudaFuncSetAttribute(remove_outlier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remove_outlier_kernel, CLOUD_THREADS, smem));
-  if (per_sm < 1) per_sm = 1;
-  int grid = ctx->sm_count * per_sm;
-  if (grid > n_clouds) grid = n_clouds;
-  int rc = ensure(ctx, ctx->scratch[SCR_MISC], (size_t)grid * b.n_max * sizeof(uint16_t));
-  if (rc != SFE_OK) return rc;
-  b.orig_ws = (uint16_t *)ctx->scratch[SCR_MISC].ptr;
-  remove_outlier_kernel<<<grid, CLOUD_THREADS, smem, ctx->stream>>>(b);
-  SFE_CUDA(cudaGetLastError());
-  ctx->launches++;
-  return SFE_OK;
+  return remove_outlier_launch(ctx, b, b.n_max, -1, b.n_max);
 }
 
 }  // namespace sfe

@@ -55,7 +55,6 @@ struct IcpBatch {
   float cell_scale;  // grid cell = cell_scale * sqrt(area / n)
   sfe_icp_params prm;
   uint16_t *orig_ws;  // [slots][nt_max]
-  float4 *seq_ws;     // [slots][ns_max] per-point terms of the sequential sums (unless flags bit 1)
   int slot_by_smid;   // workspace slot = %smid (one CTA per SM, one CTA per problem) instead of blockIdx.x
 };
 
@@ -212,22 +211,48 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
   return __uint_as_float(prefix);
 }
 
-// Exact SEQUENTIAL float32 sum of n values p[0], p[stride], ... in index order (the accumulation order of
-// oracle/icp_ref.c; default mode), computed by one warp: the 32 lanes fetch 32 consecutive terms with one
-// coalesced request (the next batch is already in flight while this one is added), and the terms are then added
-// one after the other -- a shuffle hands term j to every lane, so all lanes carry the same running sum.  The
-// dependent chain is the float add alone (~4 cycles per term); lanes beyond n contribute +0, which leaves a sum
-// unchanged bit for bit.  All 32 lanes of the warp must call this.
-__device__ __forceinline__ float seq_sum_f32_warp(const float *p, int n, int stride) {
+// Exact SEQUENTIAL float32 sums in index order (the accumulation order of oracle/icp_ref.c; default mode), computed
+// by one warp: lane j evaluates term base + j of a batch of 32, and the terms are then added one after the other --
+// a shuffle hands term j to every lane, so all lanes carry the same running sum.  The dependent chain is the float
+// add alone (~4 cycles per term); lanes beyond n contribute +0, which leaves a sum unchanged bit for bit.  All 32
+// lanes of the warp must call these.
+template <typename F>
+__device__ __forceinline__ float seq_sum_warp(int n, F term) {
   const int lane = threadIdx.x & 31;
   float s = 0.f;
-  float cur = lane < n ? p[(size_t)lane * stride] : 0.f;
   for (int base = 0; base < n; base += 32) {
-    const int nx = base + 32 + lane;
-    const float nxt = nx < n ? p[(size_t)nx * stride] : 0.f;
+    const float v = base + lane < n ? term(base + lane) : 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, cur, j));
-    cur = nxt;
+    for (int j = 0; j < 32; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
+  }
+  return s;
+}
+
+// the same over values in global memory, p[0], p[stride], ...: eight batches (256 terms) are requested at once and
+// the next eight are in flight while these are added, so the L2 latency hides behind the ~1000-cycle add chain
+__device__ __forceinline__ float seq_sum_warp_global(const float *p, int n, int stride) {
+  const int lane = threadIdx.x & 31;
+  float s = 0.f, cur[8], nxt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = k * 32 + lane;
+    cur[k] = i < n ? p[(size_t)i * stride] : 0.f;
+  }
+  for (int base = 0; base < n; base += 256) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + 256 + k * 32 + lane;
+      nxt[k] = i < n ? p[(size_t)i * stride] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (base + k * 32 < n) {  // (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, cur[k], j));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
   }
   return s;
 }
@@ -275,7 +300,6 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   // ~1e-4 closer to exact arithmetic, a few per cent faster; deviates from the oracle by up to ~2e-3 m on
   // ill-conditioned scans because the float32-sequential sums themselves are that noisy).
   const bool seq = (prm.flags & 2) == 0;
-  float4 *seq_ws = seq ? b.seq_ws + (size_t)slot * b.ns_max : nullptr;
 
   for (int p = blockIdx.x; p < b.P; p += gridDim.x) {
     const int si = b.src_id ? b.src_id[p] : p, ti = b.tgt_id ? b.tgt_id[p] : p;
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       float mx, my;
       if (seq) {
         if (tid < 64) {  // warps 0 and 1: x and y
-          const float sum = seq_sum_f32_warp(tgt + (tid >> 5), nt, 2);
+          const float sum = seq_sum_warp_global(tgt + (tid >> 5), nt, 2);
           if ((tid & 31) == 0) sh.seq[tid >> 5] = __fdiv_rn(sum, (float)nt);
         }
         __syncthreads();
@@ -584,17 +608,10 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
           bool keep = match[i] != 0xffff;
           if (prm.outlier_max_dist > 0.f) keep = keep && (dist[i] <= out_d2);
           if (prm.trim_ratio >= 0.f) keep = keep && (dist[i] <= limit);
-          if (!keep) {
-            match[i] = 0xffff;
-            seq_ws[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // x + (+0) == x: dropped pairs do not disturb the sums
-            continue;
-          }
-          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-          const float2 r = sorted[match[i]];
-          seq_ws[i] = make_float4(q.x, q.y, r.x, r.y);
-          ++cnt;
+          if (!keep) match[i] = 0xffff;
+          cnt += keep;
         }
-        n_keep = block_total(cnt, &sh.tot[0][0], tot_phase);  // (its barrier publishes seq_ws to the CTA)
+        n_keep = block_total(cnt, &sh.tot[0][0], tot_phase);  // (its barrier publishes match[])
       } else {
         double s5[5] = {0, 0, 0, 0, 0}, t5[5];
         for (int i = tid; i < ns; i += nthr) {
@@ -619,13 +636,24 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         break;
       }
       if (seq) {
-        if (tid < 128) {  // warps 0..3: one component each
-          const float sum = seq_sum_f32_warp(reinterpret_cast<const float *>(seq_ws) + (tid >> 5), ns, 4);
-          if ((tid & 31) == 0) sh.seq[tid >> 5] = sum;
+        // warps 0..3 sum one component each (step x, step y, matched reference x, y); dropped pairs add +0
+        if (tid < 128) {
+          const int comp = tid >> 5;
+          const float sum = seq_sum_warp(ns, [&](int i) -> float {
+            const int m = match[i];
+            if (m == 0xffff) return 0.f;
+            if (comp < 2) {
+              const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+              return comp == 0 ? q.x : q.y;
+            }
+            const float2 r = sorted[m];
+            return comp == 2 ? r.x : r.y;
+          });
+          if ((tid & 31) == 0) sh.seq[comp] = sum;
         }
         __syncthreads();
         mrx = sh.seq[0], mry = sh.seq[1], mfx = sh.seq[2], mfy = sh.seq[3];
-        __syncthreads();  // sh.seq and seq_ws are rewritten below
+        __syncthreads();  // sh.seq is rewritten below
       }
       const float winv = __fdiv_rn(1.0f, (float)n_keep);
       mrx = __fmul_rn(mrx, winv), mry = __fmul_rn(mry, winv);
@@ -634,21 +662,18 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       // 3d. cross-covariance of the centred pairs
       double t4[4];
       if (seq) {
-        for (int i = tid; i < ns; i += nthr) {
-          if (match[i] == 0xffff) {
-            seq_ws[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            continue;
-          }
-          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-          const float2 r = sorted[match[i]];
-          const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
-          const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
-          seq_ws[i] = make_float4(__fmul_rn(qx, px), __fmul_rn(qx, py), __fmul_rn(qy, px), __fmul_rn(qy, py));
-        }
-        __syncthreads();
         if (tid < 128) {
-          const float sum = seq_sum_f32_warp(reinterpret_cast<const float *>(seq_ws) + (tid >> 5), ns, 4);
-          if ((tid & 31) == 0) sh.seq[tid >> 5] = sum;
+          const int comp = tid >> 5;  // m00 = qx*px, m01 = qx*py, m10 = qy*px, m11 = qy*py
+          const float sum = seq_sum_warp(ns, [&](int i) -> float {
+            const int m = match[i];
+            if (m == 0xffff) return 0.f;
+            const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+            const float2 r = sorted[m];
+            const float pc = (comp & 1) ? __fsub_rn(q.y, mry) : __fsub_rn(q.x, mrx);
+            const float qc = (comp & 2) ? __fsub_rn(r.y, mfy) : __fsub_rn(r.x, mfx);
+            return __fmul_rn(qc, pc);
+          });
+          if ((tid & 31) == 0) sh.seq[comp] = sum;
         }
         __syncthreads();
         t4[0] = (double)sh.seq[0], t4[1] = (double)sh.seq[1], t4[2] = (double)sh.seq[2], t4[3] = (double)sh.seq[3];
@@ -900,11 +925,9 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   int slots = grid;
   if (per_sm == 1 && P > grid) b.slot_by_smid = 1, slots = ICP_SM_SLOTS, grid = P;  // one CTA per problem
   const size_t orig_bytes = ((size_t)slots * b.nt_max * sizeof(uint16_t) + 15) & ~size_t(15);
-  const size_t seq_bytes = (prm->flags & 2) ? 0 : (size_t)slots * b.ns_max * sizeof(float4);
-  int rc = ensure(ctx, ctx->scratch[SCR_ICP], orig_bytes + seq_bytes);
+  int rc = ensure(ctx, ctx->scratch[SCR_ICP], orig_bytes);
   if (rc != SFE_OK) return rc;
   b.orig_ws = (uint16_t *)ctx->scratch[SCR_ICP].ptr;
-  b.seq_ws = seq_bytes ? (float4 *)((char *)ctx->scratch[SCR_ICP].ptr + orig_bytes) : nullptr;
   void *args[] = {(void *)&b};
   SFE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, ctx->stream));
   ctx->launches++;

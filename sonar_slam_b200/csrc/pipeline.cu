@@ -23,9 +23,10 @@ int cfar_run(sfe_ctx *ctx, const void *img, int dtype, int F, int R, int B, int 
 int cart_points_run(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const uint32_t *bits, int F, int cap,
                     int32_t *ij, float *xy, int32_t *count);
 int downsample_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
-                   float resolution, float *out_pts, int32_t *out_idx, int32_t *out_count);
+                   float resolution, float *out_pts, int32_t *out_idx, int32_t *out_count, int n_split = 0);
 int remove_outlier_run(sfe_ctx *ctx, const float *pts, const int *off, const int *cnt, int n_clouds, int dim, int n_max,
-                       double radius, int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count);
+                       double radius, int min_points, float *out_pts, int32_t *out_idx, int32_t *out_count,
+                       int n_split = 0);
 int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const int *src_off, const int *src_cnt,
             const float *tgt_pts, const int *tgt_off, const int *tgt_cnt, int min_points, const int *src_id,
             const int *tgt_id, int P, int ns_max, int nt_max, const float *guess, float *T_out, int *iters,
@@ -38,6 +39,9 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
 // a class that leaves 14 % of the frames to the second launch (512 points) 3.11 ms -- the tail of a nearly empty
 // launch costs a full problem latency.
 constexpr int FE_ICP_SMALL_SRC = 640, FE_ICP_SMALL_TGT = 1536, FE_ICP_SMALL_THREADS = 128;
+// Size classes of the cloud filters (cloud.cu: two launches by cloud size).  Config-4 replay: 3.1-4.4 k raw Cartesian
+// points per frame, ~580 after the voxel filter, ~400 after the outlier filter, window submaps <= 1.8 k raw points.
+constexpr int FE_DS_SPLIT = 4608, FE_RO_SPLIT = 1024, FE_SUBMAP_SPLIT = 2048;
 
 // T_ab = pose_a^-1 * pose_b as float32 3x3 (gtsam Pose2::between, then matrix().astype(float32)).
 // Evaluated on the host in double (libm), so the float32 matrices the kernels see are the ones a
@@ -343,7 +347,7 @@ static int fe_features(sfe_frontend *fe, const uint8_t *frames_dev, int f0, int 
   if (p.resolution > 0.f) {
     fe_tic(fe, SFE_FE_DOWNSAMPLE);
     rc = downsample_run(ctx, cur, fe->off_pts + f0, cur_cnt + f0, n, 2, (int)cap, p.resolution, fe->xy_b, fe->idx,
-                        fe->cnt_b + f0);
+                        fe->cnt_b + f0, FE_DS_SPLIT);
     fe_toc(fe);
     if (rc != SFE_OK) return rc;
     cur = fe->xy_b, cur_cnt = fe->cnt_b;
@@ -352,7 +356,7 @@ static int fe_features(sfe_frontend *fe, const uint8_t *frames_dev, int f0, int 
     float *dst = (cur == fe->xy_a) ? fe->xy_b : fe->xy_a;
     fe_tic(fe, SFE_FE_OUTLIER);
     rc = remove_outlier_run(ctx, cur, fe->off_pts + f0, cur_cnt + f0, n, 2, (int)cap, p.outlier_radius,
-                            p.outlier_min_points, dst, fe->idx, fe->cnt_c + f0);
+                            p.outlier_min_points, dst, fe->idx, fe->cnt_c + f0, FE_RO_SPLIT);
     fe_toc(fe);
     if (rc != SFE_OK) return rc;
   }
@@ -400,7 +404,7 @@ static int fe_match(sfe_frontend *fe, int f0, int n) {
   const int32_t *tcnt = fe->tcnt_a;
   if (p.submap_resolution > 0.f) {
     int rc = downsample_run(ctx, fe->tgt_a, fe->off_tgt + f0, fe->tcnt_a + f0, n, 2, tcap, p.submap_resolution,
-                            fe->tgt_b, fe->tgt_idx, fe->tcnt_b + f0);
+                            fe->tgt_b, fe->tgt_idx, fe->tcnt_b + f0, FE_SUBMAP_SPLIT);
     if (rc != SFE_OK) return rc;
     tgt = fe->tgt_b, tcnt = fe->tcnt_b;
   }

@@ -84,6 +84,13 @@ def gather_results(local, n_halo, n_total, dst=0):
 RESULT_WORDS = 12  # T (9 float32) + iterations, inliers, status (int32) = 48 B per problem
 
 
+def _rank_world():
+    """(rank, world); (0, 1) when no process group was initialised (single-GPU use)."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def chunk_plan(P, world, chunks):
     """Every rank's shard is cut into the same number of chunks: plan[r] = [(start, end), ...] (global indices);
     a chunk may be empty.  Shared by sender and receivers so that their send/recv sizes agree."""
@@ -122,7 +129,7 @@ def _default_icp(src, tgt, guess, prm):
 def scatter_pairs(P, ns, nt, src_all=None, tgt_all=None, guess_all=None, src=0, device="cuda"):
     """One grouped send/recv: rank `src` holds src_all [P,ns,2], tgt_all [P,nt,2], guess_all [P,3,3] (float32, on
     its device); every rank returns its shard (src, tgt, guess) -- views into the originals on rank `src`."""
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world()
     s, e = shard_bounds(P, world)[rank]
     if rank == src:
         ops_ = []
@@ -145,7 +152,7 @@ def scatter_pairs(P, ns, nt, src_all=None, tgt_all=None, guess_all=None, src=0, 
 
 def gather_pair_results(local_packed, P, dst=0):
     """NCCL gather of the packed results (shards padded to the largest one); rank `dst` gets [P, RESULT_WORDS]."""
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world()
     bounds = shard_bounds(P, world)
     if world == 1:
         return local_packed
@@ -166,7 +173,7 @@ def run_pair_backlog(P, ns, nt, prm, src_all=None, tgt_all=None, guess_all=None,
     solves its own shard straight from the backlog.  Returns the packed results [P, RESULT_WORDS] on rank `src`
     (None elsewhere).  `icp_fn(src, tgt, guess, prm) -> packed` is injectable (CPU tests run this over gloo)."""
     icp_fn = icp_fn or _default_icp
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world()
     plan = chunk_plan(P, world, chunks)
     s, e = shard_bounds(P, world)[rank]
     cuda = torch.device(device).type == "cuda"

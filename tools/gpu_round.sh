@@ -26,7 +26,7 @@ for s in $steps; do
                 python tools/prof_cfar.py 4096 u8 bits > gpurun_out/${tag}_ncu_cfar_lut.log 2>&1 ;;
     ncu_icp)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:icp_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_prof_icp_config3 \
                 python tools/prof_icp.py 296 > gpurun_out/${tag}_ncu_icp.log 2>&1; tail -2 gpurun_out/${tag}_ncu_icp.log ;;
-    ncu_pipe) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"icp_kernel|feat|cart_|downsample|outlier|assemble" -s 16 -c 8 -f -o gpurun_out/${tag}_prof_pipeline \
+    ncu_pipe) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"icp_kernel|feat|cart_|downsample|outlier|assemble" -s 14 -c 7 -f -o gpurun_out/${tag}_prof_pipeline \
                 python tools/prof_pipeline.py 1024 > gpurun_out/${tag}_ncu_pipe.log 2>&1; tail -2 gpurun_out/${tag}_ncu_pipe.log ;;
     n2)       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 \
                 > gpurun_out/${tag}_bench_n2.json 2> gpurun_out/${tag}_bench_n2.err; tail -c 2500 gpurun_out/${tag}_bench_n2.json; tail -5 gpurun_out/${tag}_bench_n2.err ;;
