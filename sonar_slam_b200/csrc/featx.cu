@@ -132,40 +132,25 @@ __global__ void __launch_bounds__(FXS_THREADS)
     }
     for (int w = tid; w < cwords; w += FXS_THREADS) cm[w] = 0;
     __syncthreads();
-    // ---- list the detections (polar cell indices) in shared memory, FXS_DETCAP per round (8 per thread),
-    //      then spread (detection -> candidate pixels) work evenly over the CTA: every lane has its own
-    //      chain of loads in flight instead of a warp serialising on one detection.
+    // ---- list the detections (polar cell indices) in shared memory and spread (detection -> candidate pixels)
+    //      work evenly over the CTA: every lane has its own chain of loads in flight instead of a warp
+    //      serialising on one detection.  A thread owns words tid, tid + T, tid + 2T, ...: neighbouring words (an
+    //      arc of detections spans a few of them in a few rows) land on different threads.
     {
-      // a thread owns words tid, tid + T, tid + 2T, ...: neighbouring words (an arc of detections spans a
-      // few of them in a few rows) land on different threads
-      int w = tid;
-      uint32_t v = w < words ? sb[w] : 0u;
-      while (true) {
-        // count up to FXS_PER_THREAD of my remaining detections
-        int take = 0;
-        {
-          int wc = w;
-          uint32_t vc = v;
-          while (take < FXS_PER_THREAD) {
-            if (vc == 0u) {
-              wc += FXS_THREADS;
-              if (wc >= words) break;
-              vc = sb[wc];
-              continue;
-            }
-            vc &= vc - 1;
-            ++take;
+      int mycount = 0;
+      for (int w = tid; w < words; w += FXS_THREADS) mycount += __popc(sb[w]);
+      int total;
+      int pos = block_exclusive_scan_fx(mycount, scan_s, total);
+      if (total <= FXS_DET_SLOTS) {
+        // the usual case: every detection of the frame fits the list -- one listing pass, one expansion pass
+        for (int w = tid; w < words; w += FXS_THREADS) {
+          uint32_t v = sb[w];
+          const int y = w / wpr, x0 = (w - y * wpr) * 32;
+          while (v) {
+            const int bit = __ffs(v) - 1;
+            v &= v - 1;
+            det[pos++] = x0 + bit < B ? y * B + x0 + bit : -1;
           }
-        }
-        int total;
-        int pos = block_exclusive_scan_fx(take, scan_s, total);
-        if (total == 0) break;
-        for (int i = 0; i < take; ++i) {
-          while (v == 0u) v = sb[w += FXS_THREADS];
-          const int bit = __ffs(v) - 1;
-          v &= v - 1;
-          const int y = w / wpr, x = (w - y * wpr) * 32 + bit;
-          det[pos++] = x < B ? y * B + x : -1;
         }
         __syncthreads();
         for (int d = tid; d < total; d += FXS_THREADS) {
@@ -177,33 +162,98 @@ __global__ void __launch_bounds__(FXS_THREADS)
             if (cart_pixel_fires(tab[pix], sb, R, B, wpr)) atomicOr(&cm[pix >> 5], 1u << (pix & 31));
           }
         }
-        __syncthreads();
+      } else {
+        // very dense masks: rounds of at most FXS_PER_THREAD detections per thread
+        int w = tid;
+        uint32_t v = w < words ? sb[w] : 0u;
+        while (true) {
+          int take = 0;
+          {
+            int wc = w;
+            uint32_t vc = v;
+            while (take < FXS_PER_THREAD) {
+              if (vc == 0u) {
+                wc += FXS_THREADS;
+                if (wc >= words) break;
+                vc = sb[wc];
+                continue;
+              }
+              vc &= vc - 1;
+              ++take;
+            }
+          }
+          int pos2 = block_exclusive_scan_fx(take, scan_s, total);
+          if (total == 0) break;
+          for (int i = 0; i < take; ++i) {
+            while (v == 0u) v = sb[w += FXS_THREADS];
+            const int bit = __ffs(v) - 1;
+            v &= v - 1;
+            const int y = w / wpr, x = (w - y * wpr) * 32 + bit;
+            det[pos2++] = x < B ? y * B + x : -1;
+          }
+          __syncthreads();
+          for (int d = tid; d < total; d += FXS_THREADS) {
+            const int q = det[d];
+            if (q < 0) continue;
+            const int s0 = inv_off[q], e0 = inv_off[q + 1];
+            for (int t = s0; t < e0; ++t) {
+              const int pix = inv_idx[t];
+              if (cart_pixel_fires(tab[pix], sb, R, B, wpr)) atomicOr(&cm[pix >> 5], 1u << (pix & 31));
+            }
+          }
+          __syncthreads();
+        }
       }
     }
     __syncthreads();
-    // ---- ordered emission: every thread owns a contiguous run of Cartesian words
+    // ---- ordered emission (np.nonzero order).  First the position of every Cartesian word's first point: each
+    //      thread sums a contiguous run of words, a block scan turns the sums into offsets, and the per-word
+    //      offsets go into the (now dead) polar plane's memory.  Then the words are dealt out STRIDED -- fired
+    //      pixels cluster (a wall is a few rows of the image), and with contiguous ownership a handful of threads
+    //      did all the writing at 2 active lanes -- and every set bit is written straight to its final slot:
+    //      (row, col) and metres in one pass.
+    uint16_t *woff = reinterpret_cast<uint16_t *>(sb);  // [cwords] (2 B per word <= the polar plane when npix/16 <= R*wpr*4)
+    const bool woff_fits = (size_t)cwords * sizeof(uint16_t) <= (size_t)words * sizeof(uint32_t);
     const int per = (cwords + FXS_THREADS - 1) / FXS_THREADS;
     const int w0 = min(tid * per, cwords), w1 = min(w0 + per, cwords);
     int mine_cnt = 0;
     for (int w = w0; w < w1; ++w) mine_cnt += __popc(cm[w]);
     int total;
     int idx = block_exclusive_scan_fx(mine_cnt, scan_s, total);
-    // pass 1: pixel indices in order (cheap, but unevenly spread over threads) ...
-    int32_t *ij_f = ij + (size_t)f * cap * 2;
-    for (int w = w0; w < w1; ++w) {
-      uint32_t v = cm[w];
-      while (v) {
-        const int bit = __ffs(v) - 1;
-        v &= v - 1;
-        if (idx < cap) ij_f[2 * (size_t)idx] = w * 32 + bit;
-        ++idx;
+    if (woff_fits) {
+      for (int w = w0; w < w1; ++w) {
+        woff[w] = (uint16_t)min(idx, 65535);  // positions past the capacity are never written
+        idx += __popc(cm[w]);
       }
+      __syncthreads();
+      const int lim = min(cap, 65535);
+      for (int w = tid; w < cwords; w += FXS_THREADS) {
+        uint32_t v = cm[w];
+        int o = woff[w];
+        while (v) {
+          const int bit = __ffs(v) - 1;
+          v &= v - 1;
+          if (o < lim) cart_emit(w * 32 + bit, cols, rows, width, height, ij, xy, ((size_t)f * cap + o) * 2);
+          ++o;
+        }
+      }
+    } else {
+      // (odd geometries whose Cartesian plane is much larger than the polar one) contiguous ownership, two passes
+      int32_t *ij_f = ij + (size_t)f * cap * 2;
+      for (int w = w0; w < w1; ++w) {
+        uint32_t v = cm[w];
+        while (v) {
+          const int bit = __ffs(v) - 1;
+          v &= v - 1;
+          if (idx < cap) ij_f[2 * (size_t)idx] = w * 32 + bit;
+          ++idx;
+        }
+      }
+      __syncthreads();
+      const int n_out = min(total, cap);
+      for (int i = tid; i < n_out; i += FXS_THREADS)
+        cart_emit(ij_f[2 * (size_t)i], cols, rows, width, height, ij, xy, ((size_t)f * cap + i) * 2);
     }
-    __syncthreads();
-    // ... pass 2: (row, col) and metres, evenly spread
-    const int n_out = min(total, cap);
-    for (int i = tid; i < n_out; i += FXS_THREADS)
-      cart_emit(ij_f[2 * (size_t)i], cols, rows, width, height, ij, xy, ((size_t)f * cap + i) * 2);
     if (tid == 0) count[f] = total;
   }
 }

@@ -158,6 +158,7 @@ struct IcpShared {  // small fixed-size part of the shared state
   float hq_w[ICP_HIST], hq_z[ICP_HIST], ht_x[ICP_HIST], ht_y[ICP_HIST];
   int hn;
   float seq[4];               // results of the sequential sums
+  __align__(16) float seq_buf[2 * 4 * 36];  // staging of seq_sum4_warp
   int cnx, cny;               // coarse occupancy grid (ICP_COARSE x ICP_COARSE fine cells per coarse cell)
   uint32_t coarse[ICP_COARSE_WORDS];
 };
@@ -212,24 +213,41 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
 }
 
 // Exact SEQUENTIAL float32 sums in index order (the accumulation order of oracle/icp_ref.c; default mode), computed
-// by one warp: lane j evaluates term base + j of a batch of 32, and the terms are then added one after the other --
-// a shuffle hands term j to every lane, so all lanes carry the same running sum.  The dependent chain is the float
-// add alone (~4 cycles per term); lanes beyond n contribute +0, which leaves a sum unchanged bit for bit.  All 32
-// lanes of the warp must call these.
+// by one warp.  The dependent chain is the float add alone (~4 cycles per term); terms beyond n (or of dropped
+// pairs) are +0, which leaves a sum unchanged bit for bit.  All 32 lanes of the warp must call these.
+// Four sequential sums at once (the components of one float4 term per point), by ONE warp with few instructions:
+// lane j evaluates the four terms of point base + j and parks them, transposed, in shared memory ([component][32],
+// rows padded to 36 floats so that the four reading lanes hit different banks); lanes 0..3 then add "their"
+// component's 32 values in order (eight LDS.128 + 32 dependent adds).  ~55 warp instructions per 32 points for all
+// four sums; result: lane c (c < 4) returns the sum of component c.
+// `scratch` = [2][4][36] floats (double-buffered: a batch is written while the previous one may still be read).
 template <typename F>
-__device__ __forceinline__ float seq_sum_warp(int n, F term) {
+__device__ __forceinline__ float seq_sum4_warp(int n, float *scratch, F term4) {
   const int lane = threadIdx.x & 31;
   float s = 0.f;
-  for (int base = 0; base < n; base += 32) {
-    const float v = base + lane < n ? term(base + lane) : 0.f;
+  int it = 0;
+  for (int base = 0; base < n; base += 32, ++it) {
+    float *buf = scratch + (it & 1) * (4 * 36);
+    const float4 t = base + lane < n ? term4(base + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    buf[0 * 36 + lane] = t.x, buf[1 * 36 + lane] = t.y, buf[2 * 36 + lane] = t.z, buf[3 * 36 + lane] = t.w;
+    __syncwarp();
+    if (lane < 4) {
+      const float4 *v = reinterpret_cast<const float4 *>(buf + lane * 36);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
+      for (int k = 0; k < 8; ++k) {
+        const float4 a = v[k];
+        s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, a.x), a.y), a.z), a.w);
+      }
+    }
+    // (the buffer written two batches from now is this one: every lane passes the next batch's __syncwarp first)
   }
   return s;
 }
 
-// the same over values in global memory, p[0], p[stride], ...: eight batches (256 terms) are requested at once and
-// the next eight are in flight while these are added, so the L2 latency hides behind the ~1000-cycle add chain
+// One sequential sum over values in global memory, p[0], p[stride], ... (the reference cloud's mean, once per
+// problem): lane j holds term base + j and a shuffle hands term j to every lane, so all lanes carry the same
+// running sum; eight batches (256 terms) are requested at once and the next eight are in flight while these are
+// added, so the L2 latency hides behind the ~1000-cycle add chain
 __device__ __forceinline__ float seq_sum_warp_global(const float *p, int n, int stride) {
   const int lane = threadIdx.x & 31;
   float s = 0.f, cur[8], nxt[8];
@@ -636,20 +654,16 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         break;
       }
       if (seq) {
-        // warps 0..3 sum one component each (step x, step y, matched reference x, y); dropped pairs add +0
-        if (tid < 128) {
-          const int comp = tid >> 5;
-          const float sum = seq_sum_warp(ns, [&](int i) -> float {
+        // warp 0 forms the four sums (step x, step y, matched reference x, y); dropped pairs add +0
+        if (tid < 32) {
+          const float sum = seq_sum4_warp(ns, sh.seq_buf, [&](int i) -> float4 {
             const int m = match[i];
-            if (m == 0xffff) return 0.f;
-            if (comp < 2) {
-              const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-              return comp == 0 ? q.x : q.y;
-            }
+            if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
+            const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
             const float2 r = sorted[m];
-            return comp == 2 ? r.x : r.y;
+            return make_float4(q.x, q.y, r.x, r.y);
           });
-          if ((tid & 31) == 0) sh.seq[comp] = sum;
+          if (tid < 4) sh.seq[tid] = sum;
         }
         __syncthreads();
         mrx = sh.seq[0], mry = sh.seq[1], mfx = sh.seq[2], mfy = sh.seq[3];
@@ -662,18 +676,17 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       // 3d. cross-covariance of the centred pairs
       double t4[4];
       if (seq) {
-        if (tid < 128) {
-          const int comp = tid >> 5;  // m00 = qx*px, m01 = qx*py, m10 = qy*px, m11 = qy*py
-          const float sum = seq_sum_warp(ns, [&](int i) -> float {
+        if (tid < 32) {  // m00 = qx*px, m01 = qx*py, m10 = qy*px, m11 = qy*py
+          const float sum = seq_sum4_warp(ns, sh.seq_buf, [&](int i) -> float4 {
             const int m = match[i];
-            if (m == 0xffff) return 0.f;
+            if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
             const float2 r = sorted[m];
-            const float pc = (comp & 1) ? __fsub_rn(q.y, mry) : __fsub_rn(q.x, mrx);
-            const float qc = (comp & 2) ? __fsub_rn(r.y, mfy) : __fsub_rn(r.x, mfx);
-            return __fmul_rn(qc, pc);
+            const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
+            const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
+            return make_float4(__fmul_rn(qx, px), __fmul_rn(qx, py), __fmul_rn(qy, px), __fmul_rn(qy, py));
           });
-          if ((tid & 31) == 0) sh.seq[comp] = sum;
+          if (tid < 4) sh.seq[tid] = sum;
         }
         __syncthreads();
         t4[0] = (double)sh.seq[0], t4[1] = (double)sh.seq[1], t4[2] = (double)sh.seq[2], t4[3] = (double)sh.seq[3];
