@@ -68,6 +68,8 @@ struct sfe_maps {  // per-geometry polar->Cartesian sampling table (featx.cu)
   void *table;     // device MapEntry[rows*cols]
   int32_t *inv_off;  // device [R*B + 1]: for every polar cell, the Cartesian pixels it can light ...
   int32_t *inv_idx;  // ... as a CSR list of pixel indices
+  float *metres;     // device [cols + rows]: lateral metres of every column, then forward metres of every row
+                     // (feature_extraction.py:235-237 evaluated per column / per row in float64 on the host)
   int device;
 };
 

@@ -80,6 +80,19 @@ __device__ __forceinline__ bool cart_pixel_fires(const MapEntry e, const uint32_
   return sum >= 512;
 }
 
+// (row, col) and metres of one fired pixel from the per-geometry tables: the pixel -> metres expressions depend on
+// the column alone (lateral) and on the row alone (forward), so sfe_maps_create evaluates them once per column /
+// row with the reference's float64 operations and the kernels only look them up.
+__device__ __forceinline__ void cart_emit_lut(int pix, int cols, float inv_cols, const float *__restrict__ metres,
+                                              int32_t *ij, float *xy, size_t o) {
+  int row = __float2int_rz(__fmul_rn((float)pix, inv_cols));
+  int col = pix - row * cols;
+  if (col < 0) --row, col += cols;           // the float quotient is within one of the exact one (pix < 2^24)
+  else if (col >= cols) ++row, col -= cols;
+  *reinterpret_cast<int2 *>(ij + o) = make_int2(row, col);
+  *reinterpret_cast<float2 *>(xy + o) = make_float2(metres[cols + row], metres[col]);
+}
+
 __device__ __forceinline__ void cart_emit(int pix, int cols, int rows, double width, double height, int32_t *ij,
                                           float *xy, size_t o) {
   const int row = pix / cols, col = pix - row * cols;
@@ -104,10 +117,11 @@ __global__ void __launch_bounds__(FXS_THREADS)
     cart_scatter_kernel(const MapEntry *__restrict__ tab, const int32_t *__restrict__ inv_off,
                         const int32_t *__restrict__ inv_idx, int npix, int cols, int rows, int R, int B, int wpr,
                         const uint8_t *__restrict__ mask, const uint32_t *__restrict__ bits, int F, int cap,
-                        double width, double height, int32_t *__restrict__ ij, float *__restrict__ xy,
+                        const float *__restrict__ metres, int32_t *__restrict__ ij, float *__restrict__ xy,
                         int32_t *__restrict__ count) {
   extern __shared__ uint32_t fxs_smem[];
   __shared__ int scan_s[36];
+  const float inv_cols = 1.0f / (float)cols;
   const int words = R * wpr, cwords = (npix + 31) / 32;
   uint32_t *sb = fxs_smem;           // polar bit plane
   uint32_t *cm = fxs_smem + words;   // Cartesian bit plane
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(FXS_THREADS)
         while (v) {
           const int bit = __ffs(v) - 1;
           v &= v - 1;
-          if (o < lim) cart_emit(w * 32 + bit, cols, rows, width, height, ij, xy, ((size_t)f * cap + o) * 2);
+          if (o < lim) cart_emit_lut(w * 32 + bit, cols, inv_cols, metres, ij, xy, ((size_t)f * cap + o) * 2);
           ++o;
         }
       }
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(FXS_THREADS)
       __syncthreads();
       const int n_out = min(total, cap);
       for (int i = tid; i < n_out; i += FXS_THREADS)
-        cart_emit(ij_f[2 * (size_t)i], cols, rows, width, height, ij, xy, ((size_t)f * cap + i) * 2);
+        cart_emit_lut(ij_f[2 * (size_t)i], cols, inv_cols, metres, ij, xy, ((size_t)f * cap + i) * 2);
     }
     if (tid == 0) count[f] = total;
   }
@@ -436,7 +450,7 @@ int cart_points_run(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const 
       if (grid > F) grid = F;
       cart_scatter_kernel<<<grid, FXS_THREADS, smem, ctx->stream>>>(
           (const MapEntry *)m->table, m->inv_off, m->inv_idx, npix, m->cols, m->rows, m->R, m->B, wpr, mask, bits, F,
-          cap, m->width, m->height, ij, xy, count);
+          cap, m->metres, ij, xy, count);
       SFE_CUDA(cudaGetLastError());
       ctx->launches++;
       return SFE_OK;
@@ -516,6 +530,28 @@ static void build_inverse_lists(const std::vector<MapEntry> &tab, int R, int B, 
   for (size_t p = 0; p < n; ++p) each_tap(p, [&](size_t q) { inv_idx[cur[q]++] = (int32_t)p; });
 }
 
+// feature_extraction.py:235-237 per column / per row, float64, operation by operation (volatile: no contraction,
+// no re-association), then the float32 cast of the cloud (pybind / the ROS message)
+static void build_metre_tables(int rows, int cols, double width, double height, std::vector<float> &t) {
+  t.resize((size_t)cols + rows);
+  for (int col = 0; col < cols; ++col) {
+    volatile double half = (double)cols / 2.0;
+    volatile double x = (double)col - half;
+    x = x / half;
+    volatile double hw = width / 2.0;
+    x = x * hw;
+    x = -1.0 * x;
+    t[col] = (float)x;
+  }
+  for (int row = 0; row < rows; ++row) {
+    volatile double y = (double)row / (double)rows;
+    y = -1.0 * y;
+    y = y * height;
+    y = y + height;
+    t[(size_t)cols + row] = (float)y;
+  }
+}
+
 }  // namespace sfe
 
 using namespace sfe;
@@ -537,8 +573,12 @@ int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_ho
   const size_t n = tab.size();
   sfe_maps *m = new sfe_maps();
   m->rows = rows, m->cols = cols, m->R = R, m->B = B, m->width = width, m->height = height, m->device = ctx->device;
-  m->table = nullptr, m->inv_off = nullptr, m->inv_idx = nullptr;
+  m->table = nullptr, m->inv_off = nullptr, m->inv_idx = nullptr, m->metres = nullptr;
+  std::vector<float> metres;
+  build_metre_tables(rows, cols, width, height, metres);
   cudaError_t e = cudaMalloc(&m->table, n * sizeof(MapEntry));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&m->metres, metres.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(m->metres, metres.data(), metres.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(m->table, tab.data(), n * sizeof(MapEntry), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->inv_off, inv_off.size() * sizeof(int32_t));
   if (e == cudaSuccess)
@@ -551,6 +591,7 @@ int sfe_maps_create(sfe_ctx *ctx, const float *map_x_host, const float *map_y_ho
     if (m->table) cudaFree(m->table);
     if (m->inv_off) cudaFree(m->inv_off);
     if (m->inv_idx) cudaFree(m->inv_idx);
+    if (m->metres) cudaFree(m->metres);
     delete m;
     return SFE_ERR_CUDA;
   }
@@ -564,6 +605,7 @@ void sfe_maps_destroy(sfe_maps *m) {
   if (m->table) cudaFree(m->table);
   if (m->inv_off) cudaFree(m->inv_off);
   if (m->inv_idx) cudaFree(m->inv_idx);
+  if (m->metres) cudaFree(m->metres);
   delete m;
 }
 

@@ -221,27 +221,59 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
 // component's 32 values in order (eight LDS.128 + 32 dependent adds).  ~55 warp instructions per 32 points for all
 // four sums; result: lane c (c < 4) returns the sum of component c.
 // `scratch` = [2][4][36] floats (double-buffered: a batch is written while the previous one may still be read).
-template <typename F>
+template <bool PIPELINED, typename F>
 __device__ __forceinline__ float seq_sum4_warp(int n, float *scratch, F term4) {
   const int lane = threadIdx.x & 31;
   float s = 0.f;
-  int it = 0;
-  for (int base = 0; base < n; base += 32, ++it) {
-    float *buf = scratch + (it & 1) * (4 * 36);
-    const float4 t = base + lane < n ? term4(base + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-    buf[0 * 36 + lane] = t.x, buf[1 * 36 + lane] = t.y, buf[2 * 36 + lane] = t.z, buf[3 * 36 + lane] = t.w;
-    __syncwarp();
-    if (lane < 4) {
-      const float4 *v = reinterpret_cast<const float4 *>(buf + lane * 36);
+  if (!PIPELINED) {
+    int it = 0;
+    for (int base = 0; base < n; base += 32, ++it) {
+      float *buf = scratch + (it & 1) * (4 * 36);
+      const float4 t = base + lane < n ? term4(base + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      buf[0 * 36 + lane] = t.x, buf[1 * 36 + lane] = t.y, buf[2 * 36 + lane] = t.z, buf[3 * 36 + lane] = t.w;
+      __syncwarp();
+      if (lane < 4) {
+        const float4 *v = reinterpret_cast<const float4 *>(buf + lane * 36);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 a = v[k];
-        s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, a.x), a.y), a.z), a.w);
+        for (int k = 0; k < 8; ++k) {
+          const float4 a = v[k];
+          s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, a.x), a.y), a.z), a.w);
+        }
       }
+      // (the buffer written two batches from now is this one: every lane passes the next batch's __syncwarp first)
     }
-    // (the buffer written two batches from now is this one: every lane passes the next batch's __syncwarp first)
+    return s;
   }
-  return s;
+  // Software-pipelined form (CTA sizes with registers to spare): while lanes 0..3 add batch k from registers, all
+  // lanes evaluate and park batch k + 1, so the add chain never waits for shared memory.
+  float4 cur[8];
+  {
+    const float4 t = lane < n ? term4(lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    scratch[0 * 36 + lane] = t.x, scratch[1 * 36 + lane] = t.y, scratch[2 * 36 + lane] = t.z, scratch[3 * 36 + lane] = t.w;
+    __syncwarp();
+    const float4 *v = reinterpret_cast<const float4 *>(scratch + (lane & 3) * 36);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cur[k] = v[k];
+  }
+  int it = 1;
+  for (int base = 0; base < n; base += 32, ++it) {
+    const int nb = base + 32;
+    float *buf = scratch + (it & 1) * (4 * 36);
+    if (nb < n) {  // (warp-uniform) park the next batch
+      const float4 t = nb + lane < n ? term4(nb + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      buf[0 * 36 + lane] = t.x, buf[1 * 36 + lane] = t.y, buf[2 * 36 + lane] = t.z, buf[3 * 36 + lane] = t.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, cur[k].x), cur[k].y), cur[k].z), cur[k].w);
+    __syncwarp();
+    if (nb < n) {
+      const float4 *v = reinterpret_cast<const float4 *>(buf + (lane & 3) * 36);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cur[k] = v[k];
+    }
+  }
+  return s;  // lanes c, c + 4, c + 8, ... all hold the sum of component c
 }
 
 // One sequential sum over values in global memory, p[0], p[stride], ... (the reference cloud's mean, once per
@@ -656,7 +688,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       if (seq) {
         // warp 0 forms the four sums (step x, step y, matched reference x, y); dropped pairs add +0
         if (tid < 32) {
-          const float sum = seq_sum4_warp(ns, sh.seq_buf, [&](int i) -> float4 {
+          const float sum = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
             const int m = match[i];
             if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
@@ -677,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       double t4[4];
       if (seq) {
         if (tid < 32) {  // m00 = qx*px, m01 = qx*py, m10 = qy*px, m11 = qy*py
-          const float sum = seq_sum4_warp(ns, sh.seq_buf, [&](int i) -> float4 {
+          const float sum = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
             const int m = match[i];
             if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 q = apply_T(Ti, reading[i].x, reading[i].y);

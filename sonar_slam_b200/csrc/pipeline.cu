@@ -346,8 +346,12 @@ static int fe_features(sfe_frontend *fe, const uint8_t *frames_dev, int f0, int 
   const int32_t *cur_cnt = fe->cnt_a;
   if (p.resolution > 0.f) {
     fe_tic(fe, SFE_FE_DOWNSAMPLE);
+    static const int ds_split = [] {  // development switch: SFE_FE_DS_SPLIT=<points> (0: one launch)
+      const char *e = getenv("SFE_FE_DS_SPLIT");
+      return e ? atoi(e) : FE_DS_SPLIT;
+    }();
     rc = downsample_run(ctx, cur, fe->off_pts + f0, cur_cnt + f0, n, 2, (int)cap, p.resolution, fe->xy_b, fe->idx,
-                        fe->cnt_b + f0, FE_DS_SPLIT);
+                        fe->cnt_b + f0, ds_split);
     fe_toc(fe);
     if (rc != SFE_OK) return rc;
     cur = fe->xy_b, cur_cnt = fe->cnt_b;
