@@ -39,9 +39,12 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
 // a class that leaves 14 % of the frames to the second launch (512 points) 3.11 ms -- the tail of a nearly empty
 // launch costs a full problem latency.
 constexpr int FE_ICP_SMALL_SRC = 640, FE_ICP_SMALL_TGT = 1536, FE_ICP_SMALL_THREADS = 128;
-// Size classes of the cloud filters (cloud.cu: two launches by cloud size).  Config-4 replay: 3.1-4.4 k raw Cartesian
+// Size classes of the cloud filters (cloud.cu: two launches by cloud size).  Config-4 replay: 3-5 k raw Cartesian
 // points per frame, ~580 after the voxel filter, ~400 after the outlier filter, window submaps <= 1.8 k raw points.
-constexpr int FE_DS_SPLIT = 4608, FE_RO_SPLIT = 1024, FE_SUBMAP_SPLIT = 2048;
+// Measured (ms per 4096 frames): outlier filter 0.145 -> 0.113 and submap down-sampling 0.241 -> 0.215 with a
+// small-cloud class; the per-frame down-sampling is best left as one launch (0.79; 0.90 / 0.87 with a class
+// boundary at 4608 / 5632 points: too many frames land in the second, poorly filled launch).
+constexpr int FE_DS_SPLIT = 0, FE_RO_SPLIT = 1024, FE_SUBMAP_SPLIT = 2048;
 
 // T_ab = pose_a^-1 * pose_b as float32 3x3 (gtsam Pose2::between, then matrix().astype(float32)).
 // Evaluated on the host in double (libm), so the float32 matrices the kernels see are the ones a

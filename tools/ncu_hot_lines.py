@@ -18,8 +18,7 @@ lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path
                                                          "sonar_slam_b200", "libsonarfe.so")
 lib = os.path.abspath(lib)
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kern}"], capture_output=True,
-                     text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 # the export holds one table per kernel launch: take the first whose name matches
 start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and kern in r[1])
@@ -46,7 +45,7 @@ with tempfile.TemporaryDirectory() as td:
             m = re.match(r"\s*\.text\.(\S+):", l)
             if m:
                 cur_fn = m.group(1)
-                want = kern in cur_fn and (mangled is None or cur_fn == mangled)
+                want = all(t in cur_fn for t in re.findall(r"[A-Za-z_0-9]+", kern) if t != "int") and (mangled is None or cur_fn == mangled)
                 if want and mangled is None and len(line_of) == 0:
                     mangled = cur_fn
                 continue
