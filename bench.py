@@ -269,7 +269,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL's log is left alone (the driver counts ranks in it); it only moves off stdout, which carries the JSON line
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        if not os.environ.get("NCCL_DEBUG_FILE"):   # (NCCL prints its version line even without NCCL_DEBUG)
             os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         opts = None
         try:  # high-priority communication stream: send/recv kernels are scheduled as soon as an SM frees up

@@ -260,6 +260,80 @@ __device__ __forceinline__ int nn_search(const GridView &g, float qx, float qy, 
   return exact;
 }
 
+// ---------------------------------------------------------------- search that certifies its answer for later
+// nn_query plus a lower bound on the distance from the query to every OTHER point: the block of cells it scans is
+// at least 3x3, the second-smallest distance met inside it is tracked, and everything outside the last block
+// scanned is farther than the block's boundary.  *lb2 receives the square of that bound (min of the two).  The
+// ICP keeps it per source point: while the point has moved less than (bound - distance to its match) since this
+// search, the match is provably still the unique nearest neighbour and no search is needed (icp.cu).
+struct NNResult2 {
+  float d2, d2nd;  // smallest and second-smallest distance (over different positions)
+  int pos, tie;
+};
+
+__device__ __forceinline__ void nn_update2(float d2, int p, NNResult2 &r) {
+  if (p == r.pos) return;  // a re-scan of the current best
+  if (d2 < r.d2) {
+    r.d2nd = r.d2;  // the old best is now the runner-up (it was <= the old runner-up)
+    r.d2 = d2, r.pos = p, r.tie = 0;
+  } else {
+    r.tie |= d2 == r.d2;
+    r.d2nd = fminf(r.d2nd, d2);
+  }
+}
+
+__device__ __forceinline__ void nn_scan_block2(const GridView &g, int cx, int cy, int k, float qx, float qy, NNResult2 &r) {
+  const int xa = max(cx - k, 0), xb = min(cx + k, g.nx - 1);
+  for (int y = max(cy - k, 0); y <= min(cy + k, g.ny - 1); ++y) {
+    const int s = g.cstart[y * g.nx + xa], e = g.cstart[y * g.nx + xb + 1], last = e - 1;
+    for (int p = s; p < e; p += 4) {
+      const int p1 = min(p + 1, last), p2 = min(p + 2, last), p3 = min(p + 3, last);
+      const float2 t0 = g.pts[p], t1 = g.pts[p1], t2 = g.pts[p2], t3 = g.pts[p3];
+      const float d0 = dist2_rn(qx - t0.x, qy - t0.y), d1 = dist2_rn(qx - t1.x, qy - t1.y);
+      const float d2 = dist2_rn(qx - t2.x, qy - t2.y), d3 = dist2_rn(qx - t3.x, qy - t3.y);
+      if (fminf(fminf(d0, d1), fminf(d2, d3)) <= r.d2nd) {  // (clamped duplicates: same position, idempotent)
+        nn_update2(d0, p, r);
+        if (p1 != p) nn_update2(d1, p1, r);
+        if (p2 != p1) nn_update2(d2, p2, r);
+        if (p3 != p2) nn_update2(d3, p3, r);
+      }
+    }
+  }
+}
+
+// exact nearest neighbour (accepted only when d2 <= max_d2, like nn_query) + *lb2
+__device__ __forceinline__ NNResult nn_query_certified(const GridView &g, float qx, float qy, float max_d2, float *lb2) {
+  NNResult out;
+  out.d2 = INFINITY, out.pos = -1, out.tie = 0;
+  *lb2 = 0.f;
+  if (g.n <= 0) return out;
+  const int cx = grid_cell_coord(qx, g.ox, g.inv_cell, g.nx), cy = grid_cell_coord(qy, g.oy, g.inv_cell, g.ny);
+  const int kmax = max(g.nx, g.ny);
+  NNResult2 r;
+  r.d2 = INFINITY, r.d2nd = INFINITY, r.pos = -1, r.tie = 0;
+  int k = min(1, kmax);
+  nn_scan_block2(g, cx, cy, k, qx, qy, r);
+  float b2;
+  while (true) {
+    b2 = nn_block_bound2(g, qx, qy, cx, cy, k);
+    if (b2 == INFINITY || b2 > r.d2 || b2 > max_d2 || k >= kmax) break;  // nothing outside can beat / be accepted
+    int kk;
+    if (r.pos >= 0 && r.d2 <= max_d2) {
+      kk = (int)(sqrtf(r.d2) * g.inv_cell * 1.0001f) + 1;  // the smallest block holding every point that close
+      kk = min(max(kk, k + 1), kmax);
+    } else {
+      kk = min(2 * k, kmax);
+    }
+    nn_scan_block2(g, cx, cy, kk, qx, qy, r);
+    k = kk;
+  }
+  out.d2 = r.d2, out.pos = r.pos, out.tie = r.tie;
+  if (out.tie) nn_resolve_tie(g, cx, cy, k, qx, qy, out);
+  *lb2 = out.tie || r.tie ? 0.f : fminf(r.d2nd, b2);  // a tie certifies nothing
+  if (out.pos >= 0 && !(out.d2 <= max_d2)) out.pos = -1, out.d2 = INFINITY, *lb2 = 0.f;
+  return out;
+}
+
 // ---------------------------------------------------------------- warp-cooperative search
 // The same search as nn_search, run by ALL 32 lanes of a warp for ONE query (arguments are warp-uniform).  Long
 // searches -- a scan point far from every wall has to look at hundreds of candidates -- are the ones a warp should

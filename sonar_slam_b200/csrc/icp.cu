@@ -145,6 +145,7 @@ __device__ __forceinline__ int block_total(int v, int *scratch /* [2][16] smem *
 
 struct IcpShared {  // small fixed-size part of the shared state
   float Ti[9];
+  float Tprev[9];  // T_iter of the previous iteration (how far did every point move since?)
   float T0[9];
   float mean[2];
   float bbox[4];
@@ -313,7 +314,7 @@ template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [IcpShared][sorted float2 nt_max][cells u32][reading float2 ns_max][dist f32 ns_max][match u16 ns_max]
-  //         [prev u16 ns_max][qstate u8 ns_max]
+  //         [prev u16 ns_max][qstate u8 ns_max][slack f32 ns_max]
   IcpShared &sh = *reinterpret_cast<IcpShared *>(smem_raw);
   size_t off = (sizeof(IcpShared) + 15) & ~size_t(15);
   float2 *sorted = reinterpret_cast<float2 *>(smem_raw + off);
@@ -330,6 +331,10 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   uint16_t *prev = reinterpret_cast<uint16_t *>(smem_raw + off);  // NN of the previous iteration (search seed)
   off += sizeof(uint16_t) * (size_t)b.ns_max;
   uint8_t *qstate = reinterpret_cast<uint8_t *>(smem_raw + off);
+  off += ((size_t)b.ns_max + 3) & ~size_t(3);
+  // certified-match margin per source point (metres): every target point other than prev[i] is farther from the
+  // point's current position than (distance to prev[i]) as long as that distance stays below slack[i]
+  float *slack = reinterpret_cast<float *>(smem_raw + off);
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   int red_phase = 0, tot_phase = 0, sel_pass = 0;  // rotation counters of the one-barrier reductions (CTA-uniform)
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       float T0[9];
       mat3_mul_rn(Tinv, guess, T0);
 #pragma unroll
-      for (int i = 0; i < 9; ++i) sh.T0[i] = T0[i], sh.Ti[i] = (i % 4 == 0) ? 1.f : 0.f;
+      for (int i = 0; i < 9; ++i) sh.T0[i] = T0[i], sh.Ti[i] = sh.Tprev[i] = (i % 4 == 0) ? 1.f : 0.f;
       rot_to_quat(sh.Ti, sh.hq_w[0], sh.hq_z[0]);
       sh.ht_x[0] = 0.f, sh.ht_y[0] = 0.f;
       sh.hn = 1;
@@ -468,6 +473,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
     for (int i = tid; i < ns; i += nthr) {
       reading[i] = apply_T(sh.T0, src[2 * i], src[2 * i + 1]);
       prev[i] = 0xffff;
+      slack[i] = 0.f;
     }
     __syncthreads();
 
@@ -489,11 +495,42 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       //           quantile element, same kept pairs); the far outliers of a scan stop costing O(area).
       int n_fin = 0;
       const bool small = ns <= 2 * nthr && nt <= 4096;  // few, cheap searches: one exact pass, no pruning
+      // Certified matches.  A search that scans at least the 3x3 block also yields a lower bound L on the distance
+      // from the point to every target point OTHER than its match (grid.cuh: nn_query_certified).  The point then
+      // moves a little every iteration; by the triangle inequality every other target point stays farther than
+      // L - (path length since).  slack[i] holds that margin, shrunk by safety terms far above float32 rounding:
+      // while the distance to the old match is below it, the old match is the unique nearest neighbour -- the
+      // answer an exhaustive search would give, ties impossible -- and costs one distance instead of a search.
+      // After the first few iterations this settles almost every point of a converging scan.
+      float Tp[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Tp[i] = sh.Tprev[i];
+      auto certified = [&](int i, const float2 q, int seed, float &d2_out) -> bool {
+        const float2 qo = apply_T(Tp, reading[i].x, reading[i].y);
+        const float step = sqrtf(dist2_rn(q.x - qo.x, q.y - qo.y));
+        const float sl = slack[i] - (step * 1.00001f + 2e-5f);
+        slack[i] = sl;
+        const float2 t = sorted[seed];
+        const float d2 = dist2_rn(q.x - t.x, q.y - t.y);
+        d2_out = d2;
+        return d2 <= max_d2 && sqrtf(d2) * 1.00001f + 1e-4f < sl;
+      };
+      auto certify = [&](int i, float lb2) {  // margin after a certifying search
+        slack[i] = lb2 < 3.0e38f ? sqrtf(lb2) * 0.99999f - 1e-4f : 3.0e38f;
+      };
       if (small) {
         for (int i = tid; i < ns; i += nthr) {
           const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
           const int seed = prev[i];
-          const NNResult r = seed != 0xffff ? nn_query_seeded(g, q.x, q.y, max_d2, seed) : nn_query(g, q.x, q.y, max_d2);
+          NNResult r;
+          float d2s;
+          if (seed != 0xffff && certified(i, q, seed, d2s)) {
+            r.d2 = d2s, r.pos = seed, r.tie = 0;
+          } else {
+            float lb2;
+            r = nn_query_certified(g, q.x, q.y, max_d2, &lb2);
+            certify(i, lb2);
+          }
           dist[i] = r.d2;
           match[i] = prev[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
           n_fin += r.pos >= 0;
@@ -506,12 +543,18 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         r.d2 = INFINITY, r.pos = -1, r.tie = 0;
         int exact;
         const int seed = prev[i];
-        const float2 ts = sorted[seed != 0xffff ? seed : 0];
-        if (seed != 0xffff && dist2_rn(q.x - ts.x, q.y - ts.y) <= stop_a) {
-          r = nn_query_seeded(g, q.x, q.y, max_d2, seed);  // last iteration's match is still close: settle it now
+        float d2s = INFINITY;
+        if (seed != 0xffff && certified(i, q, seed, d2s)) {
+          r.d2 = d2s, r.pos = seed, r.tie = 0;  // provably still the nearest neighbour
+          exact = 1;
+        } else if (seed != 0xffff && d2s <= stop_a) {
+          float lb2;  // last iteration's match is still close: settle it now, with a certificate for the next ones
+          r = nn_query_certified(g, q.x, q.y, max_d2, &lb2);
+          certify(i, lb2);
           exact = 1;
         } else {
           exact = nn_search(g, q.x, q.y, max_d2, stop_a, -1, r);  // own cell, then at most the 3x3 block
+          slack[i] = 0.f;
         }
         if (exact) prev[i] = (r.pos >= 0 && r.d2 <= max_d2) ? (uint16_t)r.pos : (uint16_t)0xffff;
         const bool fin = r.pos >= 0 && r.d2 <= max_d2;
@@ -607,6 +650,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
             r.tie = 1;  // pass A did not resolve ties; a block scan below replaces this flag with what it finds
             const int exact = nn_search_warp(g, qx, qy, max_d2, stop_d2, 1, r);
             if ((tid & 31) == L) {
+              slack[i] = 0.f;  // (a cooperative search keeps no runner-up: nothing certified)
               if (exact) {
                 const bool fin = r.pos >= 0 && r.d2 <= max_d2;  // == the finiteness found in pass B
                 dist[i] = fin ? r.d2 : INFINITY;
@@ -749,7 +793,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         float Tn[9];
         mat3_mul_rn(dT, Ti, Tn);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) sh.Ti[i] = Tn[i];
+        for (int i = 0; i < 9; ++i) sh.Tprev[i] = Ti[i], sh.Ti[i] = Tn[i];
         sh.inliers = n_keep;
         const int count = ++sh.count;
         bool counter_stop = false;
@@ -920,7 +964,8 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   auto smem_for = [&](int max_cells) {
     return ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
            sizeof(uint32_t) * (size_t)((max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
-           sizeof(float) * (size_t)b.ns_max + 2 * sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 16;
+           sizeof(float) * (size_t)b.ns_max + 2 * sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 4 +
+           sizeof(float) * (size_t)b.ns_max + 16;
   };
   // big problems: trade cell-table entries (coarser cells) for room before giving up
   while (smem_for(b.max_cells) > (size_t)ctx->max_smem_optin && b.max_cells > b.nt_max / 4 + 256)
