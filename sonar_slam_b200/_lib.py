@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsonarfe.so")
+LIB_PATH = os.environ.get("SFE_LIB_PATH") or os.path.join(_HERE, "libsonarfe.so")  # (override: kernel experiments)
 
 c_int, c_double, c_void_p, c_float = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_float
 

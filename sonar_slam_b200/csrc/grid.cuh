@@ -334,6 +334,44 @@ __device__ __forceinline__ NNResult nn_query_certified(const GridView &g, float 
   return out;
 }
 
+// The seeded search with a certificate of a chosen size.  The seed (last iteration's match) is at distance d from
+// the query, so the nearest neighbour lies in the disc of radius d; scanning the cells that overlap the disc of
+// radius d + margin settles the nearest neighbour exactly (as nn_query_seeded does) AND shows that every other
+// point is farther than min(runner-up met, d + margin).  A small margin keeps the scan as narrow as the plain seeded
+// search; the caller sizes it to a few of the point's recent steps, so that one search serves several iterations.
+__device__ __forceinline__ NNResult nn_query_seeded_certified(const GridView &g, float qx, float qy, float max_d2,
+                                                              int seed, float margin, float *lb2) {
+  const float2 t = g.pts[seed];
+  const float d0 = dist2_rn(qx - t.x, qy - t.y);
+  if (!(d0 <= max_d2)) return nn_query_certified(g, qx, qy, max_d2, lb2);  // the seed is not acceptable any more
+  const float cover = sqrtf(d0) * 1.0001f + 1e-4f * g.cell + margin;  // every point within `cover` gets scanned
+  const int xa = grid_cell_coord(qx - cover, g.ox, g.inv_cell, g.nx), xb = grid_cell_coord(qx + cover, g.ox, g.inv_cell, g.nx);
+  const int ya = grid_cell_coord(qy - cover, g.oy, g.inv_cell, g.ny), yb = grid_cell_coord(qy + cover, g.oy, g.inv_cell, g.ny);
+  NNResult2 r;
+  r.d2 = INFINITY, r.d2nd = INFINITY, r.pos = -1, r.tie = 0;
+  for (int y = ya; y <= yb; ++y) {
+    const int s = g.cstart[y * g.nx + xa], e = g.cstart[y * g.nx + xb + 1], last = e - 1;
+    for (int p = s; p < e; p += 4) {
+      const int p1 = min(p + 1, last), p2 = min(p + 2, last), p3 = min(p + 3, last);
+      const float2 t0 = g.pts[p], t1 = g.pts[p1], t2 = g.pts[p2], t3 = g.pts[p3];
+      const float e0 = dist2_rn(qx - t0.x, qy - t0.y), e1 = dist2_rn(qx - t1.x, qy - t1.y);
+      const float e2 = dist2_rn(qx - t2.x, qy - t2.y), e3 = dist2_rn(qx - t3.x, qy - t3.y);
+      if (fminf(fminf(e0, e1), fminf(e2, e3)) <= r.d2nd) {
+        nn_update2(e0, p, r);
+        if (p1 != p) nn_update2(e1, p1, r);
+        if (p2 != p1) nn_update2(e2, p2, r);
+        if (p3 != p2) nn_update2(e3, p3, r);
+      }
+    }
+  }
+  NNResult out;
+  out.d2 = r.d2, out.pos = r.pos, out.tie = r.tie;  // r.pos >= 0: the seed's own cell is inside the rectangle
+  if (out.tie) nn_resolve_tie_rect(g, xa, xb, ya, yb, qx, qy, out);
+  const float c = cover * 0.9999f - 2e-4f * g.cell;  // what the rectangle certainly covers (float-safe)
+  *lb2 = r.tie ? 0.f : fminf(r.d2nd, c > 0.f ? c * c : 0.f);
+  return out;
+}
+
 // ---------------------------------------------------------------- warp-cooperative search
 // The same search as nn_search, run by ALL 32 lanes of a warp for ONE query (arguments are warp-uniform).  Long
 // searches -- a scan point far from every wall has to look at hundreds of candidates -- are the ones a warp should

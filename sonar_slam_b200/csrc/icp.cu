@@ -505,9 +505,9 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       float Tp[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) Tp[i] = sh.Tprev[i];
-      auto certified = [&](int i, const float2 q, int seed, float &d2_out) -> bool {
+      auto certified = [&](int i, const float2 q, int seed, float &d2_out, float &step) -> bool {
         const float2 qo = apply_T(Tp, reading[i].x, reading[i].y);
-        const float step = sqrtf(dist2_rn(q.x - qo.x, q.y - qo.y));
+        step = sqrtf(dist2_rn(q.x - qo.x, q.y - qo.y));
         const float sl = slack[i] - (step * 1.00001f + 2e-5f);
         slack[i] = sl;
         const float2 t = sorted[seed];
@@ -518,17 +518,21 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       auto certify = [&](int i, float lb2) {  // margin after a certifying search
         slack[i] = lb2 < 3.0e38f ? sqrtf(lb2) * 0.99999f - 1e-4f : 3.0e38f;
       };
+      // certificate size: a few of the point's steps (steps shrink as the scan converges), a fraction of a cell at most
+      auto margin_for = [&](float step) { return fminf(fmaxf(6.f * step, 0.01f * g.cell), 0.35f * g.cell); };
       if (small) {
         for (int i = tid; i < ns; i += nthr) {
           const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
           const int seed = prev[i];
           NNResult r;
-          float d2s;
-          if (seed != 0xffff && certified(i, q, seed, d2s)) {
+          float d2s, step, lb2;
+          if (seed == 0xffff) {
+            r = nn_query_certified(g, q.x, q.y, max_d2, &lb2);
+            certify(i, lb2);
+          } else if (certified(i, q, seed, d2s, step)) {
             r.d2 = d2s, r.pos = seed, r.tie = 0;
           } else {
-            float lb2;
-            r = nn_query_certified(g, q.x, q.y, max_d2, &lb2);
+            r = nn_query_seeded_certified(g, q.x, q.y, max_d2, seed, margin_for(step), &lb2);
             certify(i, lb2);
           }
           dist[i] = r.d2;
@@ -543,13 +547,13 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         r.d2 = INFINITY, r.pos = -1, r.tie = 0;
         int exact;
         const int seed = prev[i];
-        float d2s = INFINITY;
-        if (seed != 0xffff && certified(i, q, seed, d2s)) {
+        float d2s = INFINITY, step = 0.f;
+        if (seed != 0xffff && certified(i, q, seed, d2s, step)) {
           r.d2 = d2s, r.pos = seed, r.tie = 0;  // provably still the nearest neighbour
           exact = 1;
         } else if (seed != 0xffff && d2s <= stop_a) {
           float lb2;  // last iteration's match is still close: settle it now, with a certificate for the next ones
-          r = nn_query_certified(g, q.x, q.y, max_d2, &lb2);
+          r = nn_query_seeded_certified(g, q.x, q.y, max_d2, seed, margin_for(step), &lb2);
           certify(i, lb2);
           exact = 1;
         } else {

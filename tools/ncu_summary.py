@@ -1,6 +1,6 @@
 """Condense `ncu --set full` reports into the JSON kept under profiles/ (run where ncu is installed):
 
-    python tools/ncu_summary.py profiles/r01_ncu_full_summaries.json name=path.ncu-rep [name=path.ncu-rep ...]
+    python tools/ncu_summary.py profiles/r02_ncu_full_summaries.json name=path.ncu-rep[@kernel-substring] [...]
 
 One entry per report (its first kernel): launch shape, duration, DRAM bytes, issue utilisation, divergence and the
 warp-stall reasons per issued instruction -- the numbers DESIGN.md / profiles/README.md quote and bench.py's
@@ -23,9 +23,13 @@ KEEP = [
 
 
 def summarise(path):
+    """path or path@substring: the first launch whose kernel name contains the substring (default: first launch)"""
+    path, _, want = path.partition("@")
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    head, units, first = rows[0], rows[1], rows[2]
+    head, units = rows[0], rows[1]
+    ki = head.index("Kernel Name")
+    first = next(r for r in rows[2:] if want in r[ki])
     d = dict(zip(head, first))
     u = dict(zip(head, units))
     res = {"kernel": d["Kernel Name"]}
