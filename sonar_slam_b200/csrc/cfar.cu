@@ -512,11 +512,14 @@ __global__ void __launch_bounds__(CF_W, 5)
 // The four warps of a CTA only share the tiles: no CTA barrier in the loop (see cfar_block16_g).
 constexpr int CG_BEAMS = 4;
 constexpr int CG_W = CF_W * CG_BEAMS;  // beams per strip
+// Ring depth / occupancy, measured on the replay frames (ms per 4096 frames, bit-plane output): 4 stages with 3
+// CTAs per SM (155 registers) 0.463; 2 stages with 3 CTAs 0.476; 2 stages with 4 CTAs per SM (128 registers,
+// 55 KB of shared memory each) 0.439 -- the kernel is latency-bound, a fourth CTA buys more than a deeper ring.
 #ifndef SFE_CG_NS
-#define SFE_CG_NS 4    // input ring depth (stages of 16 rows x 512 beams)
+#define SFE_CG_NS 2    // input ring depth (stages of 16 rows x 512 beams)
 #endif
 #ifndef SFE_CG_MINB
-#define SFE_CG_MINB 3  // CTAs per SM the register budget is set for (4 needs SFE_CG_NS = 2 to fit shared memory)
+#define SFE_CG_MINB 4  // CTAs per SM the register budget is set for
 #endif
 constexpr int CG_NS = SFE_CG_NS;
 constexpr int CG_GMIN_LO = 16;         // below this nearly every word qualifies: use the table kernel
@@ -701,7 +704,7 @@ __device__ __forceinline__ void cfar_block16_g(CfarStepG &s, uint8_t (*tile)[2][
 }
 
 template <int ALG, bool MASK, bool BITS>
-__global__ void __launch_bounds__(CF_W, MASK ? 2 : SFE_CG_MINB)
+__global__ void __launch_bounds__(CF_W, MASK ? SFE_CG_MINB - 1 : SFE_CG_MINB)
     cfar_u8_gate4_kernel(const __grid_constant__ CUtensorMap in_map, CfarParams p, const uint16_t *__restrict__ lut_g,
                          const int lut_n, const uint32_t gate_add) {
   uint8_t(*tile)[2][CF_CH][CG_W / 2] = reinterpret_cast<uint8_t(*)[2][CF_CH][CG_W / 2]>(cg_smem);

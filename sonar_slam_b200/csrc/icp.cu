@@ -55,6 +55,7 @@ struct IcpBatch {
   float cell_scale;  // grid cell = cell_scale * sqrt(area / n)
   sfe_icp_params prm;
   uint16_t *orig_ws;  // [slots][nt_max]
+  int small_mult;     // problems with ns <= small_mult * blockDim.x (and nt <= 4096) take the one-pass exact path
   int slot_by_smid;   // workspace slot = %smid (one CTA per SM, one CTA per problem) instead of blockIdx.x
 };
 
@@ -494,14 +495,15 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       //           0 and needs no exact distance.  Results are identical to an exhaustive search (same
       //           quantile element, same kept pairs); the far outliers of a scan stop costing O(area).
       int n_fin = 0;
-      const bool small = ns <= 2 * nthr && nt <= 4096;  // few, cheap searches: one exact pass, no pruning
+      const bool small = ns <= b.small_mult * nthr && nt <= 4096;  // few, cheap searches: one exact pass, no pruning
       // Certified matches.  A search that scans at least the 3x3 block also yields a lower bound L on the distance
       // from the point to every target point OTHER than its match (grid.cuh: nn_query_certified).  The point then
       // moves a little every iteration; by the triangle inequality every other target point stays farther than
       // L - (path length since).  slack[i] holds that margin, shrunk by safety terms far above float32 rounding:
       // while the distance to the old match is below it, the old match is the unique nearest neighbour -- the
       // answer an exhaustive search would give, ties impossible -- and costs one distance instead of a search.
-      // After the first few iterations this settles almost every point of a converging scan.
+      // Used for the small problems of the front end (window submaps thinned to 0.5 m: runner-ups are decimetres
+      // away and a certificate lasts several iterations; ICP stage 2.53 -> 2.36 ms per 4096 frames).
       float Tp[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) Tp[i] = sh.Tprev[i];
@@ -547,18 +549,14 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         r.d2 = INFINITY, r.pos = -1, r.tie = 0;
         int exact;
         const int seed = prev[i];
-        float d2s = INFINITY, step = 0.f;
-        if (seed != 0xffff && certified(i, q, seed, d2s, step)) {
-          r.d2 = d2s, r.pos = seed, r.tie = 0;  // provably still the nearest neighbour
-          exact = 1;
-        } else if (seed != 0xffff && d2s <= stop_a) {
-          float lb2;  // last iteration's match is still close: settle it now, with a certificate for the next ones
-          r = nn_query_seeded_certified(g, q.x, q.y, max_d2, seed, margin_for(step), &lb2);
-          certify(i, lb2);
+        // (no certificates here: a 20 000-point target puts the runner-up a centimetre from the match, so a
+        // certificate rarely outlives an iteration -- measured 2.32 -> 2.59 ms per wave with them)
+        const float2 ts = sorted[seed != 0xffff ? seed : 0];
+        if (seed != 0xffff && dist2_rn(q.x - ts.x, q.y - ts.y) <= stop_a) {
+          r = nn_query_seeded(g, q.x, q.y, max_d2, seed);  // last iteration's match is still close: settle it now
           exact = 1;
         } else {
           exact = nn_search(g, q.x, q.y, max_d2, stop_a, -1, r);  // own cell, then at most the 3x3 block
-          slack[i] = 0.f;
         }
         if (exact) prev[i] = (r.pos >= 0 && r.d2 <= max_d2) ? (uint16_t)r.pos : (uint16_t)0xffff;
         const bool fin = r.pos >= 0 && r.d2 <= max_d2;
@@ -654,7 +652,6 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
             r.tie = 1;  // pass A did not resolve ties; a block scan below replaces this flag with what it finds
             const int exact = nn_search_warp(g, qx, qy, max_d2, stop_d2, 1, r);
             if ((tid & 31) == L) {
-              slack[i] = 0.f;  // (a cooperative search keeps no runner-up: nothing certified)
               if (exact) {
                 const bool fin = r.pos >= 0 && r.d2 <= max_d2;  // == the finiteness found in pass B
                 dist[i] = fin ? r.d2 : INFINITY;
@@ -965,6 +962,13 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   b.max_cells = pick_max_cells(b.nt_max);
   b.cell_scale = 1.0f;
   b.prm = *prm;
+  {
+    static const int mult = [] {  // development switch: SFE_ICP_SMALL_MULT
+      const char *e = getenv("SFE_ICP_SMALL_MULT");
+      return e ? atoi(e) : 2;
+    }();
+    b.small_mult = mult;
+  }
   auto smem_for = [&](int max_cells) {
     return ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
            sizeof(uint32_t) * (size_t)((max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
