@@ -963,9 +963,12 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   b.cell_scale = 1.0f;
   b.prm = *prm;
   {
+    // One-pass exact path (per-lane searches with certified matches, no pruning passes) for problems of up to
+    // 5 source points per thread: measured on the config-4 replay (sources of ~360 points, 128-thread CTAs), ICP
+    // stage per 4096 frames 2.54 ms with a limit of 2 points per thread, 2.23 with 3, 1.82 with 5.
     static const int mult = [] {  // development switch: SFE_ICP_SMALL_MULT
       const char *e = getenv("SFE_ICP_SMALL_MULT");
-      return e ? atoi(e) : 2;
+      return e ? atoi(e) : 5;
     }();
     b.small_mult = mult;
   }
