@@ -268,15 +268,35 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- this benchmark has no CPU fallback for the product path")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL's log is left alone (the driver counts ranks in it); it only moves off stdout, which carries the JSON line
-        if not os.environ.get("NCCL_DEBUG_FILE"):   # (NCCL prints its version line even without NCCL_DEBUG)
+        # NCCL's log is left alone (the driver counts ranks in it).  stdout carries the one JSON line, so whatever
+        # NCCL prints while the communicators come up (its version line, NCCL_DEBUG=INFO output) is sent to stderr:
+        # by NCCL_DEBUG_FILE where NCCL honours it, and by pointing file descriptor 1 at stderr until the first
+        # collective and the first send/recv have completed.
+        if not os.environ.get("NCCL_DEBUG_FILE"):
             os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         opts = None
         try:  # high-priority communication stream: send/recv kernels are scheduled as soon as an SM frees up
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         except Exception:  # noqa: BLE001
             opts = None
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            if rank == 0:
+                for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, warm, r) for r in range(1, world)]):
+                    q.wait()
+            else:
+                for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, warm, 0)]):
+                    q.wait()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     F, K, W = args.frames, args.steps, args.warmup
 
     # ---- synthetic bag replay for this rank (frames stay resident in HBM; > L2 by far: F*256 KiB)

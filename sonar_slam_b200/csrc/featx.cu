@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(FXS_THREADS)
     //      thread sums a contiguous run of words, a block scan turns the sums into offsets, and the per-word
     //      offsets go into the (now dead) polar plane's memory.  Then the words are dealt out STRIDED -- fired
     //      pixels cluster (a wall is a few rows of the image), and with contiguous ownership a handful of threads
-    //      did all the writing at 2 active lanes -- and every set bit is written straight to its final slot:
-    //      (row, col) and metres in one pass.
+    //      did all the writing at 2 active lanes -- and every set bit's pixel index is written to its final slot; a
+    //      dense second pass turns the indices into (row, col) and metres.
     uint16_t *woff = reinterpret_cast<uint16_t *>(sb);  // [cwords] (2 B per word <= the polar plane when npix/16 <= R*wpr*4)
     const bool woff_fits = (size_t)cwords * sizeof(uint16_t) <= (size_t)words * sizeof(uint32_t);
     const int per = (cwords + FXS_THREADS - 1) / FXS_THREADS;
@@ -240,17 +240,25 @@ __global__ void __launch_bounds__(FXS_THREADS)
         idx += __popc(cm[w]);
       }
       __syncthreads();
+      // pass 1 (strided words: balanced over threads, but the set bits of a warp's 32 words are few and uneven, so
+      // the loop body is kept to the bare minimum): the pixel index of every point goes to its final slot
       const int lim = min(cap, 65535);
+      int32_t *ij_f = ij + (size_t)f * cap * 2;
       for (int w = tid; w < cwords; w += FXS_THREADS) {
         uint32_t v = cm[w];
         int o = woff[w];
         while (v) {
           const int bit = __ffs(v) - 1;
           v &= v - 1;
-          if (o < lim) cart_emit_lut(w * 32 + bit, cols, inv_cols, metres, ij, xy, ((size_t)f * cap + o) * 2);
+          if (o < lim) ij_f[2 * (size_t)o] = w * 32 + bit;
           ++o;
         }
       }
+      __syncthreads();
+      // pass 2 (dense: every lane has a point): (row, col) and metres
+      const int n_out = min(total, lim);
+      for (int i = tid; i < n_out; i += FXS_THREADS)
+        cart_emit_lut(ij_f[2 * (size_t)i], cols, inv_cols, metres, ij, xy, ((size_t)f * cap + i) * 2);
     } else {
       // (odd geometries whose Cartesian plane is much larger than the polar one) contiguous ownership, two passes
       int32_t *ij_f = ij + (size_t)f * cap * 2;
