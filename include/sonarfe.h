@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SFE_VERSION 100
+#define SFE_VERSION 200 /* round 2: + sfe_fov_select_*, sfe_frontend_set_carry, sfe_frontend_params.flip_lateral, sfe_icp_params.flags bit 1 */
 
 #if defined(__GNUC__)
 #define SFE_API __attribute__((visibility("default")))

@@ -62,8 +62,6 @@ struct __align__(8) MapEntry {
 
 constexpr int FX_THREADS = 1024;
 constexpr int FXS_THREADS = 512;  // detection-driven variant
-constexpr int FXS_PER_THREAD = 8;                        // detections a thread lists per round
-constexpr int FXS_DET_SLOTS = FXS_PER_THREAD * FXS_THREADS;
 
 // cv2.remap's fixed-point bilinear rule for one Cartesian pixel against a 0/1 polar bit plane
 __device__ __forceinline__ bool cart_pixel_fires(const MapEntry e, const uint32_t *__restrict__ sb, int R, int B, int wpr) {
@@ -125,7 +123,7 @@ __global__ void __launch_bounds__(FXS_THREADS)
   const int words = R * wpr, cwords = (npix + 31) / 32;
   uint32_t *sb = fxs_smem;           // polar bit plane
   uint32_t *cm = fxs_smem + words;   // Cartesian bit plane
-  int32_t *det = reinterpret_cast<int32_t *>(fxs_smem + words + cwords);  // [FXS_DET_SLOTS]
+  uint32_t *doff = fxs_smem + words + cwords;  // [(words + 1) / 2]: rank of the first set bit of every pair of polar words
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = FXS_THREADS / 32;
 
   for (int f = blockIdx.x; f < F; f += gridDim.x) {
@@ -146,137 +144,79 @@ __global__ void __launch_bounds__(FXS_THREADS)
     }
     for (int w = tid; w < cwords; w += FXS_THREADS) cm[w] = 0;
     __syncthreads();
-    // ---- list the detections (polar cell indices) in shared memory and spread (detection -> candidate pixels)
-    //      work evenly over the CTA: every lane has its own chain of loads in flight instead of a warp
-    //      serialising on one detection.  A thread owns words tid, tid + T, tid + 2T, ...: neighbouring words (an
-    //      arc of detections spans a few of them in a few rows) land on different threads.
+    // ---- detections -> candidate pixels.  The set bits of the polar plane are enumerated DENSELY: a block scan
+    //      gives every pair of words the rank of its first set bit (`doff`), and thread d then finds detection d by
+    //      a binary search over those ranks plus a find-n-th-set-bit -- every lane of every warp has a detection
+    //      (walking the bits of one's own words left 4-6 lanes of 32 busy: set bits cluster in a few words).
+    //      Each detection walks its inverse list with its own chain of loads in flight.
     {
+      const int npair = (words + 1) / 2;
+      const int per = (npair + FXS_THREADS - 1) / FXS_THREADS;
+      const int k0 = min(tid * per, npair), k1 = min(k0 + per, npair);
+      auto pair_count = [&](int k) { return __popc(sb[2 * k]) + (2 * k + 1 < words ? __popc(sb[2 * k + 1]) : 0); };
       int mycount = 0;
-      for (int w = tid; w < words; w += FXS_THREADS) mycount += __popc(sb[w]);
+      for (int k = k0; k < k1; ++k) mycount += pair_count(k);
       int total;
       int pos = block_exclusive_scan_fx(mycount, scan_s, total);
-      if (total <= FXS_DET_SLOTS) {
-        // the usual case: every detection of the frame fits the list -- one listing pass, one expansion pass
-        for (int w = tid; w < words; w += FXS_THREADS) {
-          uint32_t v = sb[w];
-          const int y = w / wpr, x0 = (w - y * wpr) * 32;
-          while (v) {
-            const int bit = __ffs(v) - 1;
-            v &= v - 1;
-            det[pos++] = x0 + bit < B ? y * B + x0 + bit : -1;
-          }
+      for (int k = k0; k < k1; ++k) {
+        doff[k] = (uint32_t)pos;
+        pos += pair_count(k);
+      }
+      __syncthreads();
+      for (int d = tid; d < total; d += FXS_THREADS) {
+        int lo = 0, hi = npair;  // last pair whose first rank is <= d (pairs without bits share their successor's rank)
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (doff[mid] <= (uint32_t)d) lo = mid; else hi = mid;
         }
-        __syncthreads();
-        for (int d = tid; d < total; d += FXS_THREADS) {
-          const int q = det[d];
-          if (q < 0) continue;
-          const int s0 = inv_off[q], e0 = inv_off[q + 1];
-          for (int t = s0; t < e0; ++t) {
-            const int pix = inv_idx[t];
-            if (cart_pixel_fires(tab[pix], sb, R, B, wpr)) atomicOr(&cm[pix >> 5], 1u << (pix & 31));
-          }
-        }
-      } else {
-        // very dense masks: rounds of at most FXS_PER_THREAD detections per thread
-        int w = tid;
-        uint32_t v = w < words ? sb[w] : 0u;
-        while (true) {
-          int take = 0;
-          {
-            int wc = w;
-            uint32_t vc = v;
-            while (take < FXS_PER_THREAD) {
-              if (vc == 0u) {
-                wc += FXS_THREADS;
-                if (wc >= words) break;
-                vc = sb[wc];
-                continue;
-              }
-              vc &= vc - 1;
-              ++take;
-            }
-          }
-          int pos2 = block_exclusive_scan_fx(take, scan_s, total);
-          if (total == 0) break;
-          for (int i = 0; i < take; ++i) {
-            while (v == 0u) v = sb[w += FXS_THREADS];
-            const int bit = __ffs(v) - 1;
-            v &= v - 1;
-            const int y = w / wpr, x = (w - y * wpr) * 32 + bit;
-            det[pos2++] = x < B ? y * B + x : -1;
-          }
-          __syncthreads();
-          for (int d = tid; d < total; d += FXS_THREADS) {
-            const int q = det[d];
-            if (q < 0) continue;
-            const int s0 = inv_off[q], e0 = inv_off[q + 1];
-            for (int t = s0; t < e0; ++t) {
-              const int pix = inv_idx[t];
-              if (cart_pixel_fires(tab[pix], sb, R, B, wpr)) atomicOr(&cm[pix >> 5], 1u << (pix & 31));
-            }
-          }
-          __syncthreads();
+        int r = d - (int)doff[lo], w = 2 * lo;
+        const int c0 = __popc(sb[w]);
+        if (r >= c0) r -= c0, ++w;
+        const int bit = __fns(sb[w], 0, r + 1);
+        const int y = w / wpr, x = (w - y * wpr) * 32 + bit;
+        if (x >= B) continue;  // padding bits of the last word of a row
+        const int q = y * B + x;
+        const int s0 = inv_off[q], e0 = inv_off[q + 1];
+        for (int t = s0; t < e0; ++t) {
+          const int pix = inv_idx[t];
+          if (cart_pixel_fires(tab[pix], sb, R, B, wpr)) atomicOr(&cm[pix >> 5], 1u << (pix & 31));
         }
       }
     }
     __syncthreads();
-    // ---- ordered emission (np.nonzero order).  First the position of every Cartesian word's first point: each
-    //      thread sums a contiguous run of words, a block scan turns the sums into offsets, and the per-word
-    //      offsets go into the (now dead) polar plane's memory.  Then the words are dealt out STRIDED -- fired
-    //      pixels cluster (a wall is a few rows of the image), and with contiguous ownership a handful of threads
-    //      did all the writing at 2 active lanes -- and every set bit's pixel index is written to its final slot; a
-    //      dense second pass turns the indices into (row, col) and metres.
-    uint16_t *woff = reinterpret_cast<uint16_t *>(sb);  // [cwords] (2 B per word <= the polar plane when npix/16 <= R*wpr*4)
-    const bool woff_fits = (size_t)cwords * sizeof(uint16_t) <= (size_t)words * sizeof(uint32_t);
-    const int per = (cwords + FXS_THREADS - 1) / FXS_THREADS;
-    const int w0 = min(tid * per, cwords), w1 = min(w0 + per, cwords);
-    int mine_cnt = 0;
-    for (int w = w0; w < w1; ++w) mine_cnt += __popc(cm[w]);
-    int total;
-    int idx = block_exclusive_scan_fx(mine_cnt, scan_s, total);
-    if (woff_fits) {
-      for (int w = w0; w < w1; ++w) {
-        woff[w] = (uint16_t)min(idx, 65535);  // positions past the capacity are never written
-        idx += __popc(cm[w]);
-      }
-      __syncthreads();
-      // pass 1 (strided words: balanced over threads, but the set bits of a warp's 32 words are few and uneven, so
-      // the loop body is kept to the bare minimum): the pixel index of every point goes to its final slot
-      const int lim = min(cap, 65535);
-      int32_t *ij_f = ij + (size_t)f * cap * 2;
-      for (int w = tid; w < cwords; w += FXS_THREADS) {
-        uint32_t v = cm[w];
-        int o = woff[w];
-        while (v) {
-          const int bit = __ffs(v) - 1;
-          v &= v - 1;
-          if (o < lim) ij_f[2 * (size_t)o] = w * 32 + bit;
-          ++o;
-        }
-      }
-      __syncthreads();
-      // pass 2 (dense: every lane has a point): (row, col) and metres
-      const int n_out = min(total, lim);
-      for (int i = tid; i < n_out; i += FXS_THREADS)
-        cart_emit_lut(ij_f[2 * (size_t)i], cols, inv_cols, metres, ij, xy, ((size_t)f * cap + i) * 2);
-    } else {
-      // (odd geometries whose Cartesian plane is much larger than the polar one) contiguous ownership, two passes
-      int32_t *ij_f = ij + (size_t)f * cap * 2;
-      for (int w = w0; w < w1; ++w) {
-        uint32_t v = cm[w];
-        while (v) {
-          const int bit = __ffs(v) - 1;
-          v &= v - 1;
-          if (idx < cap) ij_f[2 * (size_t)idx] = w * 32 + bit;
-          ++idx;
-        }
+    // ---- ordered emission (np.nonzero order), dense in the same way: ranks of the Cartesian word pairs by a block
+    //      scan (they go into the polar plane's memory, dead by now), then thread j finds point j and writes
+    //      (row, col) and metres straight to slot j.
+    {
+      const int npair = (cwords + 1) / 2;
+      const int per = (npair + FXS_THREADS - 1) / FXS_THREADS;
+      const int k0 = min(tid * per, npair), k1 = min(k0 + per, npair);
+      auto pair_count = [&](int k) { return __popc(cm[2 * k]) + (2 * k + 1 < cwords ? __popc(cm[2 * k + 1]) : 0); };
+      int mine_cnt = 0;
+      for (int k = k0; k < k1; ++k) mine_cnt += pair_count(k);
+      int total;
+      int idx = block_exclusive_scan_fx(mine_cnt, scan_s, total);
+      uint32_t *woff = sb;  // [npair] <= [words]: checked by the host (else the dense kernel is used)
+      for (int k = k0; k < k1; ++k) {
+        woff[k] = (uint32_t)idx;
+        idx += pair_count(k);
       }
       __syncthreads();
       const int n_out = min(total, cap);
-      for (int i = tid; i < n_out; i += FXS_THREADS)
-        cart_emit_lut(ij_f[2 * (size_t)i], cols, inv_cols, metres, ij, xy, ((size_t)f * cap + i) * 2);
+      for (int j = tid; j < n_out; j += FXS_THREADS) {
+        int lo = 0, hi = npair;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (woff[mid] <= (uint32_t)j) lo = mid; else hi = mid;
+        }
+        int r = j - (int)woff[lo], w = 2 * lo;
+        const int c0 = __popc(cm[w]);
+        if (r >= c0) r -= c0, ++w;
+        const int bit = __fns(cm[w], 0, r + 1);
+        cart_emit_lut(w * 32 + bit, cols, inv_cols, metres, ij, xy, ((size_t)f * cap + j) * 2);
+      }
+      if (tid == 0) count[f] = total;
     }
-    if (tid == 0) count[f] = total;
   }
 }
 
@@ -449,8 +389,10 @@ int cart_points_run(sfe_ctx *ctx, const sfe_maps *m, const uint8_t *mask, const 
   // detection-driven kernel whenever both bit planes fit in shared memory
   {
     const int wpr = (m->B + 31) / 32, npix = m->rows * m->cols;
-    const size_t smem = sizeof(uint32_t) * ((size_t)m->R * wpr + (size_t)(npix + 31) / 32 + FXS_DET_SLOTS);
-    if (m->inv_off != nullptr && smem <= (size_t)ctx->max_smem_optin - 2048 && !ctx_force_gather(ctx)) {
+    const size_t pw = (size_t)m->R * wpr, cw = (size_t)(npix + 31) / 32;
+    const size_t smem = sizeof(uint32_t) * (pw + cw + (pw + 1) / 2 + 1);
+    // (the emission's rank table of Cartesian word pairs reuses the polar plane: it must fit there)
+    if (m->inv_off != nullptr && smem <= (size_t)ctx->max_smem_optin - 2048 && (cw + 1) / 2 <= pw && !ctx_force_gather(ctx)) {
       SFE_CUDA(cudaFuncSetAttribute(cart_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 1;
       SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cart_scatter_kernel, FXS_THREADS, smem));

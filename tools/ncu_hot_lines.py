@@ -14,6 +14,8 @@ import tempfile
 from collections import defaultdict
 
 rep, kern = os.path.abspath(sys.argv[1]), sys.argv[2]
+kern, _, nth = kern.partition("#")   # "name#k": the k-th launch (0-based) whose kernel name contains `name`
+nth = int(nth) if nth else 0
 lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                          "sonar_slam_b200", "libsonarfe.so")
 lib = os.path.abspath(lib)
@@ -21,7 +23,7 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 # the export holds one table per kernel launch: take the first whose name matches
-start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and kern in r[1])
+start = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and kern in r[1]][nth]
 head = rows[start + 1]
 body = []
 for r in rows[start + 2:]:
