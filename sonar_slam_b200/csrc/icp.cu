@@ -55,6 +55,7 @@ struct IcpBatch {
   float cell_scale;  // grid cell = cell_scale * sqrt(area / n)
   sfe_icp_params prm;
   uint16_t *orig_ws;  // [slots][nt_max]
+  int use_order;      // search passes visit the source points in spatially sorted order (big problems only)
   int small_mult;     // problems with ns <= small_mult * blockDim.x (and nt <= 4096) take the one-pass exact path
   int slot_by_smid;   // workspace slot = %smid (one CTA per SM, one CTA per problem) instead of blockIdx.x
 };
@@ -315,7 +316,7 @@ template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [IcpShared][sorted float2 nt_max][cells u32][reading float2 ns_max][dist f32 ns_max][match u16 ns_max]
-  //         [prev u16 ns_max][qstate u8 ns_max][slack f32 ns_max]
+  //         [prev u16 ns_max][qstate u8 ns_max][slack f32 ns_max][order u16 ns_max]
   IcpShared &sh = *reinterpret_cast<IcpShared *>(smem_raw);
   size_t off = (sizeof(IcpShared) + 15) & ~size_t(15);
   float2 *sorted = reinterpret_cast<float2 *>(smem_raw + off);
@@ -336,6 +337,11 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   // certified-match margin per source point (metres): every target point other than prev[i] is farther from the
   // point's current position than (distance to prev[i]) as long as that distance stays below slack[i]
   float *slack = reinterpret_cast<float *>(smem_raw + off);
+  off += sizeof(float) * (size_t)b.ns_max;
+  // processing order of the source points in the search passes: sorted by a coarse cell of the target grid, so that
+  // the lanes of a warp look at neighbouring cells (similar amounts of work, the same shared-memory lines); results
+  // are stored by point index and the sums run in point order, so the order is invisible in the results
+  uint16_t *order = reinterpret_cast<uint16_t *>(smem_raw + off);
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   int red_phase = 0, tot_phase = 0, sel_pass = 0;  // rotation counters of the one-barrier reductions (CTA-uniform)
@@ -477,6 +483,38 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       slack[i] = 0.f;
     }
     __syncthreads();
+    if (b.use_order) {  // counting sort of the point indices by a 16 x 16 bucket grid over the target's bounding box.  Counters: the
+       // radix-select histogram that the next selection pass neither fills nor expects to be clear (pass p fills
+       // hist[p % 3] and clears hist[(p + 1) % 3]; hist[(p + 2) % 3] is cleared by pass p + 1 before it is used)
+      int *cnt = sh.hist[(sel_pass + 2) % 3];
+      for (int h = tid; h < 256; h += nthr) cnt[h] = 0;
+      __syncthreads();
+      const float bw = fmaxf(sh.bbox[2] - sh.bbox[0], 1e-6f) * (1.f / 16.f), bh = fmaxf(sh.bbox[3] - sh.bbox[1], 1e-6f) * (1.f / 16.f);
+      auto bucket = [&](int i) {
+        const int bx = min(max((int)((reading[i].x - sh.bbox[0]) / bw), 0), 15);
+        const int by = min(max((int)((reading[i].y - sh.bbox[1]) / bh), 0), 15);
+        return by * 16 + bx;
+      };
+      for (int i = tid; i < ns; i += nthr) atomicAdd(&cnt[bucket(i)], 1);
+      __syncthreads();
+      if (tid < 32) {  // exclusive scan of the 256 counters by one warp (8 per lane)
+        int c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = cnt[tid * 8 + j], sum += c[j];
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (tid >= d) incl += t;
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cnt[tid * 8 + j] = run, run += c[j];
+      }
+      __syncthreads();
+      for (int i = tid; i < ns; i += nthr) order[atomicAdd(&cnt[bucket(i)], 1)] = (uint16_t)i;
+      __syncthreads();
+    }
 
     // ---- 3. iterations
     while (true) {
@@ -523,7 +561,8 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       // certificate size: a few of the point's steps (steps shrink as the scan converges), a fraction of a cell at most
       auto margin_for = [&](float step) { return fminf(fmaxf(6.f * step, 0.01f * g.cell), 0.35f * g.cell); };
       if (small) {
-        for (int i = tid; i < ns; i += nthr) {
+        for (int ii = tid; ii < ns; ii += nthr) {
+          const int i = b.use_order ? order[ii] : ii;
           const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
           const int seed = prev[i];
           NNResult r;
@@ -543,7 +582,8 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         }
       }
       const float stop_a = (0.999f * g.cell) * (0.999f * g.cell);
-      for (int i = tid; i < ns && !small; i += nthr) {
+      for (int ii = tid; ii < ns && !small; ii += nthr) {
+        const int i = b.use_order ? order[ii] : ii;
         const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
         NNResult r;
         r.d2 = INFINITY, r.pos = -1, r.tie = 0;
@@ -566,7 +606,8 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         n_fin += fin;
       }
       // pass B: finiteness of the points that have no candidate yet
-      for (int i = tid; i < ns && !small; i += nthr) {
+      for (int ii = tid; ii < ns && !small; ii += nthr) {
+        const int i = b.use_order ? order[ii] : ii;
         if (qstate[i] & 4) continue;
         const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
         int verdict = -1;  // 1 finite, 0 not, -1 unknown
@@ -631,7 +672,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         // the unsettled points are few (the scan's outliers) and their searches long: every warp takes the
         // unsettled points of its 32 lanes one after the other and searches for each with all 32 lanes
         for (int i0 = tid & ~31; i0 < ns; i0 += nthr) {
-          const int i = i0 + (tid & 31);
+          const int i = i0 + (tid & 31) < ns ? (b.use_order ? (int)order[i0 + (tid & 31)] : i0 + (tid & 31)) : ns;
           const bool mine = i < ns && !(qstate[i] & 1);
           float2 q = make_float2(0.f, 0.f);
           int cand = -1;
@@ -960,6 +1001,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   b.T_out = T_out, b.iters = iters, b.inliers = inliers, b.status = status;
   b.P = P, b.ns_max = ns_max > 0 ? ns_max : 1, b.nt_max = nt_max > 0 ? nt_max : 1;
   b.max_cells = pick_max_cells(b.nt_max);
+  b.use_order = b.ns_max > 1024;  // (the front end's 640-point class is sized to 6 CTAs per SM to the byte)
   b.cell_scale = 1.0f;
   b.prm = *prm;
   {
@@ -976,7 +1018,7 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
     return ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
            sizeof(uint32_t) * (size_t)((max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
            sizeof(float) * (size_t)b.ns_max + 2 * sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 4 +
-           sizeof(float) * (size_t)b.ns_max + 16;
+           sizeof(float) * (size_t)b.ns_max + (b.use_order ? sizeof(uint16_t) * (size_t)b.ns_max : 0) + 16;
   };
   // big problems: trade cell-table entries (coarser cells) for room before giving up
   while (smem_for(b.max_cells) > (size_t)ctx->max_smem_optin && b.max_cells > b.nt_max / 4 + 256)
