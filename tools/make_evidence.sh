@@ -16,8 +16,11 @@ args=""
 [ -f $G/${tag}_prof_cfar_u8lut.ncu-rep ] && args="$args prof_cfar_u8lut=$G/${tag}_prof_cfar_u8lut.ncu-rep"
 [ -f $G/${tag}_prof_icp_config3.ncu-rep ] && args="$args prof_icp_config3=$G/${tag}_prof_icp_config3.ncu-rep"
 if [ -f $G/${tag}_prof_pipeline.ncu-rep ]; then
-  for k in cart_scatter downsample remove_outlier assemble "icp_kernel<(int)128"; do
-    n=$(echo $k | tr -cd 'a-z0-9_'); args="$args pipeline_$n=$G/${tag}_prof_pipeline.ncu-rep@$k"; done
+  args="$args pipeline_cart_scatter=$G/${tag}_prof_pipeline.ncu-rep@cart_scatter"
+  args="$args pipeline_downsample_frames=$G/${tag}_prof_pipeline.ncu-rep@downsample#2"
+  args="$args pipeline_downsample_submaps=$G/${tag}_prof_pipeline.ncu-rep@downsample#0"
+  args="$args pipeline_remove_outlier=$G/${tag}_prof_pipeline.ncu-rep@remove_outlier"
+  args="$args pipeline_icp_128=$G/${tag}_prof_pipeline.ncu-rep@icp_kernel<128"
 fi
 [ -n "$args" ] && python tools/ncu_summary.py $P/${rnd}_ncu_full_summaries.json $args
 {
@@ -26,7 +29,7 @@ fi
   [ -f $G/${tag}_prof_icp_config3.ncu-rep ] && python tools/ncu_hot_lines.py $G/${tag}_prof_icp_config3.ncu-rep icp_kernel sonar_slam_b200/libsonarfe.so 20
   if [ -f $G/${tag}_prof_pipeline.ncu-rep ]; then
     python tools/ncu_hot_lines.py $G/${tag}_prof_pipeline.ncu-rep cart_scatter sonar_slam_b200/libsonarfe.so 14
-    python tools/ncu_hot_lines.py $G/${tag}_prof_pipeline.ncu-rep downsample sonar_slam_b200/libsonarfe.so 14
+    python tools/ncu_hot_lines.py $G/${tag}_prof_pipeline.ncu-rep "downsample#2" sonar_slam_b200/libsonarfe.so 14
     python tools/ncu_hot_lines.py $G/${tag}_prof_pipeline.ncu-rep "icp_kernel<(int)128" sonar_slam_b200/libsonarfe.so 20
   fi
 } > $P/${rnd}_hot_lines.txt 2>&1 || true
@@ -34,7 +37,7 @@ fi
 {
   echo "# cuobjdump -sass sonar_slam_b200/libsonarfe.so -- cfar_u8_gate4_kernel<SOCA, bits>: one interior 16-row block"
   echo "# (rows are branch-free: LDS.32 of 4 beams, PRMT to 16-bit lanes, IADD3 window sums, VIMNMX.U16x2, gate test, predicated parking)"
-  cuobjdump -sass -fun '_ZN3sfe20cfar_u8_gate4_kernelILi1ELb0ELb1EEEv14CUtensorMap_stNS_10CfarParamsEPKtij' sonar_slam_b200/libsonarfe.so \
+  cuobjdump -sass -fun '_ZN3sfe20cfar_u8_gate4_kernelILi1ELb0ELb1EEEv14CUtensorMap_stNS_10CfarParamsEPKtij' sonar_slam_b200/libsonarfe.so 2>/dev/null \
     | grep -E '^\s+/\*[0-9a-f]{4}\*/' | sed -E 's/\s+\/\* 0x[0-9a-f]+ \*\///' > /tmp/_g4.txt
   first=$(grep -n "SYNCS.PHASECHK" /tmp/_g4.txt | sed -n 3p | cut -d: -f1)
   sed -n "${first},$((first+150))p" /tmp/_g4.txt

@@ -25,11 +25,13 @@ KEEP = [
 def summarise(path):
     """path or path@substring: the first launch whose kernel name contains the substring (default: first launch)"""
     path, _, want = path.partition("@")
+    want, _, nth = want.partition("#")   # kernel-substring#k: the k-th such launch (0-based)
+    nth = int(nth) if nth else 0
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
     head, units = rows[0], rows[1]
     ki = head.index("Kernel Name")
-    first = next(r for r in rows[2:] if want in r[ki])
+    first = [r for r in rows[2:] if want in r[ki]][nth]
     d = dict(zip(head, first))
     u = dict(zip(head, units))
     res = {"kernel": d["Kernel Name"]}
