@@ -232,8 +232,14 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
         for (int a = a0; a < a1; ++a) mine += is_head(a) ? 1 : 0;
         int total;
         int rank = block_exclusive_scan(mine, scan, total);
-        for (int a = a0; a < a1; ++a) {
-          if (!is_head(a)) continue;
+        // the heads park their position in the output slot of their leaf ...
+        for (int a = a0; a < a1; ++a)
+          if (is_head(a)) b.out_idx[(size_t)o + rank++] = a;
+        __syncthreads();
+        // ... and the leaves are then finished densely, one per thread (a head per lane left 2-3 lanes of 32 busy in
+        // the medoid search: 16 % of this kernel's instructions); slot r is read and rewritten by the same thread
+        for (int r = tid; r < total; r += nthr) {
+          const int a = b.out_idx[(size_t)o + r];
           int e0;
           if (wide) {
             const unsigned ka = key32[sidx[a]];
@@ -247,10 +253,9 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
           for (int m = a; m < e0; ++m)
             if (facc[m] < best) best = facc[m], med = m;
           const int idx = sidx[med];
-          const size_t dst = (size_t)(o + rank);
+          const size_t dst = (size_t)(o + r);
           for (int d = 0; d < b.dim; ++d) b.out_pts[dst * b.dim + d] = pts[(size_t)idx * b.dim + d];
           b.out_idx[dst] = idx;
-          ++rank;
         }
         if (tid == 0) b.out_count[cl] = total;
       }

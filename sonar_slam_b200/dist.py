@@ -116,6 +116,15 @@ def unpack_results(packed):
                 inliers=packed[:, 10], status=packed[:, 11])
 
 
+_STREAMS = {}
+
+
+def _side_streams(dev):
+    if dev not in _STREAMS:
+        _STREAMS[dev] = (torch.cuda.Stream(dev), [torch.cuda.Stream(dev), torch.cuda.Stream(dev)])
+    return _STREAMS[dev]
+
+
 def _default_icp(src, tgt, guess, prm):
     """src [n, ns, 2], tgt [n, nt, 2], guess [n,3,3] cuda tensors -> packed results [n, RESULT_WORDS]."""
     from . import ops
@@ -184,12 +193,20 @@ def run_pair_backlog(P, ns, nt, prm, src_all=None, tgt_all=None, guess_all=None,
                 local[a - s:b - s] = icp_fn(src_all[a:b], tgt_all[a:b], guess_all[a:b], prm)
         return local
     compute = torch.cuda.current_stream() if cuda else None
-    comm = torch.cuda.Stream() if cuda else None
+    # the pieces are solved on two alternating streams: a piece is one launch of one CTA per problem, and its last,
+    # partly filled wave of CTAs would otherwise idle most SMs once per piece (8 pieces: ~10 ms of a 145 ms shard).
+    # (the side streams are created once per device and reused: libsonarfe contexts are cached per stream)
+    comm, solve = _side_streams(torch.cuda.current_device()) if cuda else (None, [None, None])
     if cuda:
         comm.wait_stream(compute)
+        for st in solve:
+            st.wait_stream(compute)
 
     def on_comm():
         return torch.cuda.stream(comm) if cuda else _Null()
+
+    def on_solve(c):
+        return torch.cuda.stream(solve[c & 1]) if cuda else _Null()
 
     if rank == src:
         # stream every other rank's pieces out, chunk by chunk (one NCCL group per chunk), while solving our own
@@ -205,7 +222,8 @@ def run_pair_backlog(P, ns, nt, prm, src_all=None, tgt_all=None, guess_all=None,
                     q.wait()
             a, b = plan[src][c]
             if b > a:
-                local[a - s:b - s] = icp_fn(src_all[a:b], tgt_all[a:b], guess_all[a:b], prm)
+                with on_solve(c):
+                    local[a - s:b - s] = icp_fn(src_all[a:b], tgt_all[a:b], guess_all[a:b], prm)
     else:
         # The whole shard is received into its final place (memory is not the constraint: 176 KB per pair), every
         # piece as its own grouped recv posted up front on the communication stream: the sender never waits for a
@@ -230,9 +248,13 @@ def run_pair_backlog(P, ns, nt, prm, src_all=None, tgt_all=None, guess_all=None,
             a, b = plan[rank][c]
             if b <= a:
                 continue
-            if cuda:
-                compute.wait_event(ready[c])
-            local[a - s:b - s] = icp_fn(sb[a - s:b - s], tb[a - s:b - s], gb[a - s:b - s], prm)
+            with on_solve(c):
+                if cuda:
+                    solve[c & 1].wait_event(ready[c])
+                local[a - s:b - s] = icp_fn(sb[a - s:b - s], tb[a - s:b - s], gb[a - s:b - s], prm)
+    if cuda:
+        for st in solve:
+            compute.wait_stream(st)
     if cuda:
         compute.wait_stream(comm)
     return gather_pair_results(local, P, dst=src)
