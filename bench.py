@@ -26,8 +26,9 @@ iterations, window of 3 previous frames).  One step = one batch through sfe_fron
 
 Multi-GPU: one process per GPU (torchrun).  The headline `value` shards frames by rank (weak scaling: F frames
 per GPU per step) with no collective on the data path; config5 is the path with a real exchange (scatter of pair
-batches from rank 0, gather of SE(2) results).  NCCL's own log is not suppressed: when NCCL_DEBUG is set and
-NCCL_DEBUG_FILE is not, it is sent to stderr so that stdout stays the one JSON line.
+batches from rank 0, gather of SE(2) results).  NCCL's own log is not suppressed or redirected by environment;
+what it prints on stdout while communicators come up or go down is diverted to stderr (file descriptor level) so
+that stdout stays the one JSON line.
 """
 import argparse
 import json
@@ -268,12 +269,10 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- this benchmark has no CPU fallback for the product path")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL's log is left alone (the driver counts ranks in it).  stdout carries the one JSON line, so whatever
-        # NCCL prints while the communicators come up (its version line, NCCL_DEBUG=INFO output) is sent to stderr:
-        # by NCCL_DEBUG_FILE where NCCL honours it, and by pointing file descriptor 1 at stderr until the first
-        # collective and the first send/recv have completed.
-        if not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # NCCL's log is left alone (NCCL_DEBUG / NCCL_DEBUG_FILE are whatever the caller set; the driver counts ranks
+        # in it).  stdout carries the one JSON line, so what NCCL prints there while the communicators come up (its
+        # version line, NCCL_DEBUG=INFO output) is sent to stderr by pointing file descriptor 1 at stderr until the
+        # first collective and the first send/recv have completed -- and again after the JSON line is out.
         opts = None
         try:  # high-priority communication stream: send/recv kernels are scheduled as soon as an SM frees up
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
@@ -515,6 +514,8 @@ def run_ours(args):
                 line["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        sys.stdout.flush()
+        os.dup2(2, 1)  # communicator tear-down messages (NCCL_DEBUG=INFO) must not follow the JSON line on stdout
         dist.destroy_process_group()
 
 
