@@ -285,12 +285,13 @@ def run_ours(args):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
             warm = torch.zeros(1, device="cuda")
             dist.all_reduce(warm)
-            if rank == 0:
+            if rank == 0:  # both directions of every (0, r) pair: the scatter's sends and the gather's
                 for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, warm, r) for r in range(1, world)]):
                     q.wait()
             else:
                 for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, warm, 0)]):
                     q.wait()
+            dist.gather(warm, [torch.zeros(1, device="cuda") for _ in range(world)] if rank == 0 else None, dst=0)
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
