@@ -153,6 +153,7 @@ struct IcpShared {  // small fixed-size part of the shared state
   float bbox[4];
   int iterate, status, count, inliers;
   int sel_bin, sel_k;
+  uint32_t sel_val;  // radix select: the element found alone in its bin
   int hist[3][256];  // radix-select histograms, used in rotation (block_select_kth)
   int scan[36];
   int tot[2][16];
@@ -208,9 +209,20 @@ __device__ __forceinline__ float block_select_kth(const float *vals, int n, int 
     const unsigned hit = __ballot_sync(0xffffffffu, kk - base < ij) & 0xffu;
     const int j = hit ? __ffs(hit) - 1 : 7;
     const int bin = src * 8 + j;
-    kk = kk - base - (__shfl_sync(0xffffffffu, ij, j) - __shfl_sync(0xffffffffu, cj, j));
+    const int in_bin = __shfl_sync(0xffffffffu, cj, j);
+    kk = kk - base - (__shfl_sync(0xffffffffu, ij, j) - in_bin);
     prefix |= (uint32_t)bin << shift;
     mask |= 255u << shift;
+    if (in_bin == 1 && shift > 0) {
+      // the wanted element is alone in its bin: no need to resolve its remaining bits digit by digit -- the one
+      // thread that holds it publishes it (typically after two of the four passes for a few hundred values)
+      for (int i = tid; i < n; i += nthr) {
+        const float v = vals[i];
+        if (v < INFINITY && (__float_as_uint(v) & mask) == prefix) sh.sel_val = __float_as_uint(v);
+      }
+      __syncthreads();
+      return __uint_as_float(sh.sel_val);  // (next written after at least one more barrier)
+    }
   }
   return __uint_as_float(prefix);
 }
