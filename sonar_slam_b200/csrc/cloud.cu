@@ -199,20 +199,23 @@ __global__ void __launch_bounds__(CLOUD_THREADS) downsample_kernel(const CloudBa
           while (e < e0 && key32[sidx[e]] == ka) ++e;
           s0 = s, e0 = e;
         }
-        const float ax = pts[(size_t)ia * b.dim], ay = pts[(size_t)ia * b.dim + 1];
+        // (dim == 2 on this path -- checked by the host: one 8-byte load per point)
+        const float2 *p2 = reinterpret_cast<const float2 *>(pts);
+        const float2 pa = p2[ia];
+        const float ax = pa.x, ay = pa.y;
         float sum = 0.f;
         int q = s0;
         for (; q + 4 <= e0; q += 4) {  // four members per trip: loads and square roots overlap, the sum stays in order
-          const int i0 = sidx[q], i1 = sidx[q + 1], i2 = sidx[q + 2], i3 = sidx[q + 3];
-          const float d0 = sqrtf(dist2_rn(ax - pts[(size_t)i0 * b.dim], ay - pts[(size_t)i0 * b.dim + 1]));
-          const float d1 = sqrtf(dist2_rn(ax - pts[(size_t)i1 * b.dim], ay - pts[(size_t)i1 * b.dim + 1]));
-          const float d2 = sqrtf(dist2_rn(ax - pts[(size_t)i2 * b.dim], ay - pts[(size_t)i2 * b.dim + 1]));
-          const float d3 = sqrtf(dist2_rn(ax - pts[(size_t)i3 * b.dim], ay - pts[(size_t)i3 * b.dim + 1]));
+          const float2 t0 = p2[sidx[q]], t1 = p2[sidx[q + 1]], t2 = p2[sidx[q + 2]], t3 = p2[sidx[q + 3]];
+          const float d0 = sqrtf(dist2_rn(ax - t0.x, ay - t0.y));
+          const float d1 = sqrtf(dist2_rn(ax - t1.x, ay - t1.y));
+          const float d2 = sqrtf(dist2_rn(ax - t2.x, ay - t2.y));
+          const float d3 = sqrtf(dist2_rn(ax - t3.x, ay - t3.y));
           sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, d0), d1), d2), d3);
         }
         for (; q < e0; ++q) {
-          const int iq = sidx[q];
-          sum = __fadd_rn(sum, sqrtf(dist2_rn(ax - pts[(size_t)iq * b.dim], ay - pts[(size_t)iq * b.dim + 1])));
+          const float2 t = p2[sidx[q]];
+          sum = __fadd_rn(sum, sqrtf(dist2_rn(ax - t.x, ay - t.y)));
         }
         facc[a] = sum;
       }

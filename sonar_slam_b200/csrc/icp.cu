@@ -56,6 +56,7 @@ struct IcpBatch {
   sfe_icp_params prm;
   uint16_t *orig_ws;  // [slots][nt_max]
   int use_order;      // search passes visit the source points in spatially sorted order (big problems only)
+  float margin_mult;  // certificate size in units of the point's last step (one-pass path)
   int small_mult;     // problems with ns <= small_mult * blockDim.x (and nt <= 4096) take the one-pass exact path
   int slot_by_smid;   // workspace slot = %smid (one CTA per SM, one CTA per problem) instead of blockIdx.x
 };
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         slack[i] = lb2 < 3.0e38f ? sqrtf(lb2) * 0.99999f - 1e-4f : 3.0e38f;
       };
       // certificate size: a few of the point's steps (steps shrink as the scan converges), a fraction of a cell at most
-      auto margin_for = [&](float step) { return fminf(fmaxf(6.f * step, 0.01f * g.cell), 0.35f * g.cell); };
+      auto margin_for = [&](float step) { return fminf(fmaxf(b.margin_mult * step, 0.01f * g.cell), 0.35f * g.cell); };
       if (small) {
         for (int ii = tid; ii < ns; ii += nthr) {
           const int i = b.use_order ? order[ii] : ii;
@@ -1025,6 +1026,11 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
       return e ? atoi(e) : 5;
     }();
     b.small_mult = mult;
+    static const float mm = [] {  // development switch: SFE_ICP_MARGIN_MULT
+      const char *e = getenv("SFE_ICP_MARGIN_MULT");
+      return e ? (float)atof(e) : 6.f;
+    }();
+    b.margin_mult = mm;
   }
   auto smem_for = [&](int max_cells) {
     return ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
