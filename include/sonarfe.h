@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define SFE_VERSION 200 /* round 2: + sfe_fov_select_*, sfe_frontend_set_carry, sfe_frontend_params.flip_lateral, sfe_icp_params.flags bit 1 */
+#define SFE_VERSION 201 /* round 2: + sfe_fov_select_*, sfe_frontend_set_carry, sfe_frontend_params.flip_lateral, sfe_icp_params.flags bit 1;
+                            201: + sfe_icp_params.minimizer / normals_knn (point-to-plane, icp.yaml:18-19) */
 
 #if defined(__GNUC__)
 #define SFE_API __attribute__((visibility("default")))
@@ -184,6 +185,14 @@ typedef struct {
                                     (oracle/icp_ref.c) -- results are bit-identical to it.  The float64 mode is a few
                                     per cent faster and closer to exact arithmetic, but differs from the float32 chain by
                                     up to ~2e-3 m on ill-conditioned scans (tests/test_icp_parity_gpu.py). */
+  int minimizer;          /* errorMinimizer: 0 PointToPointErrorMinimizer (shipped, icp.yaml:20)
+                             1 PointToPlaneErrorMinimizer force2D (the alternative the YAML keeps commented out,
+                               icp.yaml:18-19): per iteration the 3x3 normal equations of sum ((R q + t - r).n)^2
+                               linearised in (theta, tx, ty), solved by Cholesky; the step is Rotation2D(theta), (tx, ty) */
+  int normals_knn;        /* point-to-plane only: the reference's normals, as a SurfaceNormalDataPointsFilter{knn}
+                             in referenceDataPointsFilters would attach them (libpointmatcher default 5; 3..16):
+                             smaller-eigenvalue direction of the covariance of each point's knn nearest reference
+                             points (itself included) */
 } sfe_icp_params;
 SFE_API void sfe_icp_params_default(sfe_icp_params *p);
 

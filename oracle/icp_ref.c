@@ -28,6 +28,20 @@
  *     |translation step| over the last `smooth` steps; stop when both fall below the limits.
  *  4. result = T_refIn_refMean * T_iter * (T_refIn_refMean^-1 * T_init).
  *
+ * X1 -- the minimiser the YAML keeps commented out (icp.yaml:18-19 `PointToPlaneErrorMinimizer force2D 1`),
+ * selected by orc_icp_params.minimizer = 1.  It needs a "normals" descriptor on the reference, which upstream
+ * comes from a `SurfaceNormalDataPointsFilter` in referenceDataPointsFilters (knn, default 5):
+ *   normals  for every reference point: its knn nearest reference points (itself included, ascending squared
+ *            float32 distance, ties by lower index); mean = sum / k; C = sum (p-mean)(p-mean)^T / k; normal = unit
+ *            eigenvector of the smaller eigenvalue of C (closed form for the symmetric 2x2; upstream calls
+ *            Eigen::EigenSolver, whose sign and rounding are build details -- the fit is invariant to the sign);
+ *            C == 0 (all neighbours coincide): normal stays (0,0) like upstream's rank test.  Computed in the
+ *            centred frame (upstream: before centring; normals do not depend on a translation).
+ *   fit      over the kept pairs (step point q, matched reference r, its normal n):  c = q.x n.y - q.y n.x,
+ *            F = (c, n.x, n.y),  A = sum F F^T,  b = -sum F ((q-r).n),  A x = b by Cholesky (A.llt()),
+ *            T_step = [Rotation2D(x0) | (x1, x2)]  (PointToPlane.cpp compute_in_place, 2-D branch).
+ *            A pivot that is not positive leaves that unknown at 0 (upstream: minimum-norm solution).
+ *
  * Every sum over points is a sequential float32 sum in point order (upstream sums with Eigen's
  * vectorised reductions, whose order is a build detail); products a*b+c are NOT contracted
  * (-ffp-contract=off) to mirror an SSE2 build.
@@ -51,6 +65,8 @@ typedef struct {
   float min_diff_trans;    /* ... minDiffTransErr (0.1) */
   int smooth_length;       /* ... smoothLength (4); 0 disables the differential checker */
   int flags;               /* bit 0: MaxDist filter compares the squared distance with maxDist itself */
+  int minimizer;           /* 0 PointToPointErrorMinimizer (shipped), 1 PointToPlaneErrorMinimizer force2D (X1) */
+  int normals_knn;         /* SurfaceNormalDataPointsFilter knn on the reference (5) */
 } orc_icp_params;
 
 enum { ORC_ICP_OK = 0, ORC_ICP_NO_OUTLIER = 1, ORC_ICP_NO_POINT = 2, ORC_ICP_NAN_ROT = 3, ORC_ICP_NAN_TRANS = 4,
@@ -91,6 +107,70 @@ static void rot_to_quat(const float *T, float *qw, float *qz) {
   }
 }
 
+/* SurfaceNormalDataPointsFilter (knn, keepNormals) on a 2-D cloud; brute-force neighbours */
+void orc_surface_normals(const float *pts, int n, int knn, float *normals) {
+  enum { KMAX = 32 };
+  if (knn > KMAX) knn = KMAX;
+  if (knn < 1) knn = 1;
+  for (int i = 0; i < n; ++i) {
+    float bd[KMAX];
+    int bi[KMAX], k = 0;
+    const float qx = pts[2 * i], qy = pts[2 * i + 1];
+    for (int j = 0; j < n; ++j) {
+      const float dx = qx - pts[2 * j], dy = qy - pts[2 * j + 1];
+      const float d2 = dx * dx + dy * dy;
+      if (k == knn && !(d2 < bd[k - 1])) continue; /* j ascending: an equal distance never displaces a lower index */
+      int at = k < knn ? k++ : knn - 1;
+      while (at > 0 && d2 < bd[at - 1]) bd[at] = bd[at - 1], bi[at] = bi[at - 1], --at;
+      bd[at] = d2, bi[at] = j;
+    }
+    float sx = 0.f, sy = 0.f;
+    for (int j = 0; j < k; ++j) sx += pts[2 * bi[j]], sy += pts[2 * bi[j] + 1];
+    const float kf = (float)k, mx = sx / kf, my = sy / kf;
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const float ux = pts[2 * bi[j]] - mx, uy = pts[2 * bi[j] + 1] - my;
+      a += ux * ux, b += ux * uy, c += uy * uy;
+    }
+    a /= kf, b /= kf, c /= kf;
+    float nx = 0.f, ny = 0.f;
+    if (a != 0.f || b != 0.f || c != 0.f) {
+      /* major axis u of [[a b][b c]]: (r + d, b) if d >= 0 else (b, r - d), d = (a-c)/2, r = sqrt(d^2 + b^2);
+       * the normal is u turned by 90 degrees; isotropic (r == 0): Eigen's identity basis, first column */
+      const float d = 0.5f * (a - c), r = sqrtf(d * d + b * b);
+      if (r == 0.f) {
+        nx = 1.f, ny = 0.f;
+      } else {
+        const float ux = d >= 0.f ? r + d : b, uy = d >= 0.f ? b : r - d;
+        const float len = sqrtf(ux * ux + uy * uy);
+        nx = -(uy / len), ny = ux / len;
+      }
+    }
+    normals[2 * i] = nx, normals[2 * i + 1] = ny;
+  }
+}
+
+/* x = A^-1 b for the symmetric 3x3 A (upper triangle a00 a01 a02 a11 a12 a22) by Cholesky, float32 */
+static void solve_llt3(const float *A, const float *b, float *x) {
+  const float a00 = A[0], a01 = A[1], a02 = A[2], a11 = A[3], a12 = A[4], a22 = A[5];
+  float l00 = 0.f, l10 = 0.f, l20 = 0.f, l11 = 0.f, l21 = 0.f, l22 = 0.f;
+  const int p0 = a00 > 0.f;
+  if (p0) l00 = sqrtf(a00), l10 = a01 / l00, l20 = a02 / l00;
+  const float d1 = a11 - l10 * l10;
+  const int p1 = d1 > 0.f;
+  if (p1) l11 = sqrtf(d1), l21 = (a12 - l20 * l10) / l11;
+  const float d2 = (a22 - l20 * l20) - l21 * l21;
+  const int p2 = d2 > 0.f;
+  if (p2) l22 = sqrtf(d2);
+  /* L y = b, L^T x = y; an unknown whose pivot failed stays 0 */
+  const float y0 = p0 ? b[0] / l00 : 0.f;
+  const float y1 = p1 ? (b[1] - l10 * y0) / l11 : 0.f;
+  const float y2 = p2 ? ((b[2] - l20 * y0) - l21 * y1) / l22 : 0.f;
+  x[2] = p2 ? y2 / l22 : 0.f;
+  x[1] = p1 ? (y1 - l21 * x[2]) / l11 : 0.f;
+  x[0] = p0 ? ((y0 - l10 * x[1]) - l20 * x[2]) / l00 : 0.f;
+}
+
 int orc_icp(const float *src, int ns, const float *tgt, int nt, const float *guess /* 3x3 row-major */,
             const orc_icp_params *prm, float *T_out, int *iters_out, int *inliers_out) {
   memcpy(T_out, guess, 9 * sizeof(float));
@@ -109,6 +189,11 @@ int orc_icp(const float *src, int ns, const float *tgt, int nt, const float *gue
   float *ref = (float *)malloc(sizeof(float) * 2 * (size_t)nt);
   for (int i = 0; i < nt; ++i) ref[2 * i] = tgt[2 * i] - mx, ref[2 * i + 1] = tgt[2 * i + 1] - my;
   nn_grid *grid = nn_grid_build(ref, nt);
+  float *normals = NULL;
+  if (prm->minimizer == 1) {
+    normals = (float *)malloc(sizeof(float) * 2 * (size_t)nt);
+    orc_surface_normals(ref, nt, prm->normals_knn, normals);
+  }
 
   /* 2. reading into the centred frame: T_refMean_dataIn = [I | -mean] * T_init */
   const float Tmean[9] = {1, 0, mx, 0, 1, my, 0, 0, 1}, Tmean_inv[9] = {1, 0, -mx, 0, 1, -my, 0, 0, 1};
@@ -184,6 +269,24 @@ int orc_icp(const float *src, int ns, const float *tgt, int nt, const float *gue
       break;
     }
     inliers = n_keep;
+    float dT[9];
+    if (prm->minimizer == 1) {
+      float A[6] = {0, 0, 0, 0, 0, 0}, bb[3] = {0, 0, 0}, x[3];
+      for (int i = 0; i < ns; ++i) {
+        if (match[i] < 0) continue;
+        const float qx = step[2 * i], qy = step[2 * i + 1];
+        const float nx = normals[2 * match[i]], ny = normals[2 * match[i] + 1];
+        const float cr = qx * ny - qy * nx;
+        const float dp = (qx - ref[2 * match[i]]) * nx + (qy - ref[2 * match[i] + 1]) * ny;
+        A[0] += cr * cr, A[1] += cr * nx, A[2] += cr * ny, A[3] += nx * nx, A[4] += nx * ny, A[5] += ny * ny;
+        bb[0] += cr * dp, bb[1] += nx * dp, bb[2] += ny * dp;
+      }
+      bb[0] = -bb[0], bb[1] = -bb[1], bb[2] = -bb[2];
+      solve_llt3(A, bb, x);
+      const float c = (float)cos((double)x[0]), s = (float)sin((double)x[0]);
+      const float d[9] = {c, -s, x[1], s, c, x[2], 0, 0, 1};
+      memcpy(dT, d, sizeof(d));
+    } else {
     const float winv = 1.0f / (float)n_keep;
     const float mrx = srx * winv, mry = sry * winv, mfx = sfx * winv, mfy = sfy * winv;
     float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f;
@@ -198,7 +301,9 @@ int orc_icp(const float *src, int ns, const float *tgt, int nt, const float *gue
     float c = 1.f, s = 0.f;
     if (h > 0.f) c = a / h, s = b / h;
     const float tx = mfx - (c * mrx + (-s) * mry), ty = mfy - (s * mrx + c * mry);
-    const float dT[9] = {c, -s, tx, s, c, ty, 0, 0, 1};
+    const float d[9] = {c, -s, tx, s, c, ty, 0, 0, 1};
+    memcpy(dT, d, sizeof(d));
+    }
     mat3_mul(dT, Ti, Ti);
 
     /* checkers: Counter first, then Differential */
@@ -248,6 +353,6 @@ int orc_icp(const float *src, int ns, const float *tgt, int nt, const float *gue
     mat3_mul(tmp, T0, T_out);
   }
   nn_grid_free(grid);
-  free(ref), free(reading), free(step), free(dist), free(sorted), free(match);
+  free(ref), free(reading), free(step), free(dist), free(sorted), free(match), free(normals);
   return status;
 }

@@ -103,12 +103,13 @@ class IcpParams(ctypes.Structure):
     _fields_ = [("matcher_max_dist", ctypes.c_float), ("outlier_max_dist", ctypes.c_float),
                 ("trim_ratio", ctypes.c_float), ("max_iterations", ctypes.c_int),
                 ("min_diff_rot", ctypes.c_float), ("min_diff_trans", ctypes.c_float),
-                ("smooth_length", ctypes.c_int), ("flags", ctypes.c_int)]
+                ("smooth_length", ctypes.c_int), ("flags", ctypes.c_int), ("minimizer", ctypes.c_int),
+                ("normals_knn", ctypes.c_int)]
 
     def __init__(self, matcher_max_dist=10.0, outlier_max_dist=3.0, trim_ratio=0.8, max_iterations=40,
-                 min_diff_rot=0.01, min_diff_trans=0.1, smooth_length=4, flags=0):
+                 min_diff_rot=0.01, min_diff_trans=0.1, smooth_length=4, flags=0, minimizer=0, normals_knn=5):
         super().__init__(matcher_max_dist, outlier_max_dist, trim_ratio, max_iterations, min_diff_rot,
-                         min_diff_trans, smooth_length, flags)
+                         min_diff_trans, smooth_length, flags, minimizer, normals_knn)
 
 
 ICP_MESSAGES = {0: "success", 1: "no outlier to filter", 2: "ErrorMnimizer: no point to minimize",
@@ -153,6 +154,16 @@ def downsample(pts, resolution):
     m = lib.orc_downsample(_p(pts, ctypes.c_float), len(pts), ctypes.c_float(resolution), _p(idx, ctypes.c_int32))
     idx = idx[:m].copy()
     return pts[idx], idx
+
+
+def surface_normals(pts, knn=5):
+    """SurfaceNormalDataPointsFilter(knn) on a 2-D cloud -> unit normals float32 [N,2] (orc_surface_normals)."""
+    lib = _load_port()
+    pts = _f32(pts)
+    out = np.zeros((len(pts), 2), np.float32)
+    lib.orc_surface_normals.restype = None
+    lib.orc_surface_normals(_p(pts, ctypes.c_float), len(pts), int(knn), _p(out, ctypes.c_float))
+    return out
 
 
 def icp(src, tgt, guess=None, params=None):

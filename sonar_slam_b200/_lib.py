@@ -118,12 +118,12 @@ class IcpParams(ctypes.Structure):
     """sfe_icp_params (include/sonarfe.h); defaults = bruce_slam/config/icp.yaml."""
     _fields_ = [("matcher_max_dist", c_float), ("outlier_max_dist", c_float), ("trim_ratio", c_float),
                 ("max_iterations", c_int), ("min_diff_rot", c_float), ("min_diff_trans", c_float),
-                ("smooth_length", c_int), ("flags", c_int)]
+                ("smooth_length", c_int), ("flags", c_int), ("minimizer", c_int), ("normals_knn", c_int)]
 
     def __init__(self, matcher_max_dist=10.0, outlier_max_dist=3.0, trim_ratio=0.8, max_iterations=40,
-                 min_diff_rot=0.01, min_diff_trans=0.1, smooth_length=4, flags=0):
+                 min_diff_rot=0.01, min_diff_trans=0.1, smooth_length=4, flags=0, minimizer=0, normals_knn=5):
         super().__init__(matcher_max_dist, outlier_max_dist, trim_ratio, max_iterations, min_diff_rot,
-                         min_diff_trans, smooth_length, flags)
+                         min_diff_trans, smooth_length, flags, minimizer, normals_knn)
 
 
 FrontendParams._fields_ = [

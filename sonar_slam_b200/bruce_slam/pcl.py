@@ -90,7 +90,8 @@ def match(mat_ref, mat_in, knn, max_dist):
 
 
 # ------------------------------------------------------------------------------------------ ICP
-_SUPPORTED = "only the module chain of the shipped bruce_slam/config/icp.yaml is implemented"
+_SUPPORTED = ("only the module chain of the shipped bruce_slam/config/icp.yaml is implemented, plus its commented-out "
+              "PointToPlaneErrorMinimizer with a SurfaceNormalDataPointsFilter on the reference")
 
 
 def parse_icp_yaml(text):
@@ -107,9 +108,20 @@ def parse_icp_yaml(text):
         raise ValueError(f"ICP yaml: cannot parse module {node!r}")
 
     prm = _lib.IcpParams(outlier_max_dist=-1.0, trim_ratio=-1.0, max_iterations=40, smooth_length=0)
-    for key in ("readingDataPointsFilters", "referenceDataPointsFilters"):
-        if cfg.get(key):
-            raise NotImplementedError(f"ICP yaml: {key} are not supported ({_SUPPORTED})")
+    if cfg.get("readingDataPointsFilters"):
+        raise NotImplementedError(f"ICP yaml: readingDataPointsFilters are not supported ({_SUPPORTED})")
+    have_normals = False
+    for node in cfg.get("referenceDataPointsFilters") or []:
+        name, p = one(node)
+        # the one reference filter point-to-plane needs: it attaches the "normals" descriptor
+        if name != "SurfaceNormalDataPointsFilter" or float(p.get("epsilon", 0)) != 0:
+            raise NotImplementedError(f"ICP yaml: reference filter {name} {p} ({_SUPPORTED})")
+        if not int(p.get("keepNormals", 1)):
+            continue
+        prm.normals_knn = int(p.get("knn", 5))
+        if not 3 <= prm.normals_knn <= 16:
+            raise NotImplementedError(f"ICP yaml: SurfaceNormalDataPointsFilter knn {prm.normals_knn} (3..16)")
+        have_normals = True
     name, p = one(cfg.get("matcher", "KDTreeMatcher"))
     if name != "KDTreeMatcher" or int(p.get("knn", 1)) != 1 or float(p.get("epsilon", 0)) != 0:
         raise NotImplementedError(f"ICP yaml: matcher {name} {p} ({_SUPPORTED})")
@@ -123,9 +135,15 @@ def parse_icp_yaml(text):
         else:
             raise NotImplementedError(f"ICP yaml: outlier filter {name} ({_SUPPORTED})")
     name, p = one(cfg.get("errorMinimizer", "PointToPointErrorMinimizer"))
-    if name != "PointToPointErrorMinimizer":
-        raise NotImplementedError(f"ICP yaml: error minimizer {name} ({_SUPPORTED}; icp.yaml:17-20 selects "
-                                  "PointToPointErrorMinimizer)")
+    if name == "PointToPlaneErrorMinimizer":  # icp.yaml:18-19 (commented out upstream); 2-D clouds: force2D is moot
+        if not have_normals:
+            # libpointmatcher: DataPoints::getDescriptorViewByName throws InvalidField at the first iteration
+            raise ValueError("ICP yaml: PointToPlaneErrorMinimizer needs the reference's normals "
+                             "(InvalidField: Cannot find descriptor normals): add a SurfaceNormalDataPointsFilter "
+                             "to referenceDataPointsFilters")
+        prm.minimizer = 1
+    elif name != "PointToPointErrorMinimizer":
+        raise NotImplementedError(f"ICP yaml: error minimizer {name} ({_SUPPORTED})")
     prm.max_iterations = 40
     for node in cfg.get("transformationCheckers") or []:
         name, p = one(node)

@@ -342,6 +342,8 @@ void sfe_icp_params_default(sfe_icp_params *p) {
   p->min_diff_trans = 0.1f;
   p->smooth_length = 4;
   p->flags = 0;
+  p->minimizer = 0;
+  p->normals_knn = 5;
 }
 
 const char *sfe_icp_status_message(int status) {

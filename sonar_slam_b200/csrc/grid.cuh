@@ -478,4 +478,65 @@ __device__ __forceinline__ NNResult nn_query_seeded(const GridView &g, float qx,
   return r;  // r.pos >= 0: the seed's own cell is inside the rectangle
 }
 
+// ---- surface normals (point-to-plane minimiser, icp.yaml:18-19 + a SurfaceNormalDataPointsFilter{knn} on the
+// reference; statement: oracle/icp_ref.c orc_surface_normals).  For the grid point at sorted position p: its knn
+// nearest grid points (itself included) in ascending (squared distance, original index) order, found ring by ring
+// around its cell until the k-th distance is below the bound of everything outside the rings scanned; then mean,
+// 2x2 covariance and the unit eigenvector of the smaller eigenvalue in closed form -- every operation a float32
+// IEEE operation in the oracle's order, so the normals are bit-identical to the oracle's.
+constexpr int GRID_KNN_MAX = 16;
+__device__ inline float2 grid_surface_normal(const GridView &g, int p, int knn) {
+  const float2 q = g.pts[p];
+  const int cx = grid_cell_coord(q.x, g.ox, g.inv_cell, g.nx), cy = grid_cell_coord(q.y, g.oy, g.inv_cell, g.ny);
+  float bd[GRID_KNN_MAX];
+  int bi[GRID_KNN_MAX];
+  int k = 0;
+  auto offer = [&](int s, int e) {
+    for (int j = s; j < e; ++j) {
+      const float2 t = g.pts[j];
+      const float d2 = dist2_rn(q.x - t.x, q.y - t.y);
+      if (k == knn) {
+        if (d2 > bd[k - 1]) continue;
+        if (d2 == bd[k - 1] && g.orig[j] > g.orig[bi[k - 1]]) continue;
+      }
+      int at = k < knn ? k++ : knn - 1;
+      while (at > 0 && (d2 < bd[at - 1] || (d2 == bd[at - 1] && g.orig[j] < g.orig[bi[at - 1]]))) {
+        bd[at] = bd[at - 1], bi[at] = bi[at - 1];
+        --at;
+      }
+      bd[at] = d2, bi[at] = j;
+    }
+  };
+  for (int kr = 0;; ++kr) {
+    const int x0 = cx - kr, x1 = cx + kr, y0 = cy - kr, y1 = cy + kr;
+    for (int y = max(y0, 0); y <= min(y1, g.ny - 1); ++y) {
+      const int row = y * g.nx;
+      if (y == y0 || y == y1) {
+        offer(g.cstart[row + max(x0, 0)], g.cstart[row + min(x1, g.nx - 1) + 1]);
+      } else {
+        if (x0 >= 0) offer(g.cstart[row + x0], g.cstart[row + x0 + 1]);
+        if (x1 <= g.nx - 1) offer(g.cstart[row + x1], g.cstart[row + x1 + 1]);
+      }
+    }
+    const float b2 = nn_block_bound2(g, q.x, q.y, cx, cy, kr);
+    if (b2 == INFINITY || (k == knn && bd[k - 1] < b2)) break;
+  }
+  float sx = 0.f, sy = 0.f;
+  for (int j = 0; j < k; ++j) sx = __fadd_rn(sx, g.pts[bi[j]].x), sy = __fadd_rn(sy, g.pts[bi[j]].y);
+  const float kf = (float)k, mx = __fdiv_rn(sx, kf), my = __fdiv_rn(sy, kf);
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int j = 0; j < k; ++j) {
+    const float ux = __fsub_rn(g.pts[bi[j]].x, mx), uy = __fsub_rn(g.pts[bi[j]].y, my);
+    a = __fadd_rn(a, __fmul_rn(ux, ux)), b = __fadd_rn(b, __fmul_rn(ux, uy)), c = __fadd_rn(c, __fmul_rn(uy, uy));
+  }
+  a = __fdiv_rn(a, kf), b = __fdiv_rn(b, kf), c = __fdiv_rn(c, kf);
+  if (a == 0.f && b == 0.f && c == 0.f) return make_float2(0.f, 0.f);
+  const float d = __fmul_rn(0.5f, __fsub_rn(a, c));
+  const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b)));
+  if (r == 0.f) return make_float2(1.f, 0.f);
+  const float ux = d >= 0.f ? __fadd_rn(r, d) : b, uy = d >= 0.f ? b : __fsub_rn(r, d);
+  const float len = __fsqrt_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)));
+  return make_float2(-__fdiv_rn(uy, len), __fdiv_rn(ux, len));
+}
+
 }  // namespace sfe

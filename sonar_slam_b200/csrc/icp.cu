@@ -55,6 +55,7 @@ struct IcpBatch {
   float cell_scale;  // grid cell = cell_scale * sqrt(area / n)
   sfe_icp_params prm;
   uint16_t *orig_ws;  // [slots][nt_max]
+  float2 *nrm_ws;     // [slots][nt_max] point-to-plane only: normal of the target point at every sorted position
   int use_order;      // search passes visit the source points in spatially sorted order (big problems only)
   float margin_mult;  // certificate size in units of the point's last step (one-pass path)
   int small_mult;     // problems with ns <= small_mult * blockDim.x (and nt <= 4096) take the one-pass exact path
@@ -325,7 +326,9 @@ __device__ __forceinline__ float seq_sum_warp_global(const float *p, int n, int 
 
 // One instantiation per CTA size so that the register budget follows the launch shape (a single
 // __launch_bounds__(512) build capped the 128-thread class at 64 registers and spilled).
-template <int THREADS, int MINB>
+// PLANE: errorMinimizer = PointToPlaneErrorMinimizer (sfe_icp_params.minimizer 1); a separate instantiation so that
+// the shipped point-to-point kernels keep their register allocation.
+template <int THREADS, int MINB, bool PLANE>
 __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [IcpShared][sorted float2 nt_max][cells u32][reading float2 ns_max][dist f32 ns_max][match u16 ns_max]
@@ -475,6 +478,16 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         sh.cnx = 0;  // too many coarse cells: the test is skipped
       }
       __syncthreads();
+    }
+
+    // ---- 1b. point-to-plane: normals of the (centred) target, one thread per sorted position, kept in global
+    // memory (8 B per target point; the iterations gather them through L2)
+    float2 *nrm = nullptr;
+    if constexpr (PLANE) {
+      nrm = b.nrm_ws + (size_t)slot * b.nt_max;
+      const int knn = min(max(prm.normals_knn, 1), GRID_KNN_MAX);
+      for (int j = tid; j < nt; j += nthr) nrm[j] = grid_surface_normal(g, j, knn);
+      // (published to the CTA by the barriers of step 2)
     }
 
     // ---- 2. reading into the centred frame; T_iter = I; checker history
@@ -750,7 +763,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
 
       // 3c. kept pairs: count and sums for the means
       int n_keep;
-      float mrx, mry, mfx, mfy;
+      float mrx = 0.f, mry = 0.f, mfx = 0.f, mfy = 0.f;
       if (seq) {
         int cnt = 0;
         for (int i = tid; i < ns; i += nthr) {
@@ -784,66 +797,144 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         __syncthreads();
         break;
       }
-      if (seq) {
-        // warp 0 forms the four sums (step x, step y, matched reference x, y); dropped pairs add +0
-        if (tid < 32) {
-          const float sum = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
-            const int m = match[i];
-            if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
-            const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-            const float2 r = sorted[m];
-            return make_float4(q.x, q.y, r.x, r.y);
-          });
-          if (tid < 4) sh.seq[tid] = sum;
+      double t4[4] = {0, 0, 0, 0};
+      float pl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // PLANE: A00 A01 A02 A11 A12 A22, sum F (q-r).n (thread 0)
+      if constexpr (PLANE) {
+        // 3c'/3d'. point-to-plane normal equations over the kept pairs (oracle/icp_ref.c, minimizer 1):
+        //   c = q.x n.y - q.y n.x,  F = (c, n.x, n.y),  A = sum F F^T,  b = -sum F ((q - r).n)
+        auto terms = [&](int i, float (&v)[9]) {
+          const int m = match[i];
+          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+          const float2 r = sorted[m];
+          const float2 n = nrm[m];
+          const float cr = __fsub_rn(__fmul_rn(q.x, n.y), __fmul_rn(q.y, n.x));
+          const float dp = __fadd_rn(__fmul_rn(__fsub_rn(q.x, r.x), n.x), __fmul_rn(__fsub_rn(q.y, r.y), n.y));
+          v[0] = __fmul_rn(cr, cr), v[1] = __fmul_rn(cr, n.x), v[2] = __fmul_rn(cr, n.y), v[3] = __fmul_rn(n.x, n.x);
+          v[4] = __fmul_rn(n.x, n.y), v[5] = __fmul_rn(n.y, n.y), v[6] = __fmul_rn(cr, dp), v[7] = __fmul_rn(n.x, dp);
+          v[8] = __fmul_rn(n.y, dp);
+        };
+        if (seq) {
+          if (tid < 32) {  // three passes of four sequential sums; dropped pairs add +0
+            float keep3[3];
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              keep3[pass] = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
+                if (match[i] == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
+                float v[9];
+                terms(i, v);
+                return pass == 0 ? make_float4(v[0], v[1], v[2], v[3])
+                                 : (pass == 1 ? make_float4(v[4], v[5], v[6], v[7]) : make_float4(v[8], 0.f, 0.f, 0.f));
+              });
+              __syncwarp();
+            }
+            if (tid < 4) sh.seq_buf[tid] = keep3[0], sh.seq_buf[4 + tid] = keep3[1], sh.seq_buf[8 + tid] = keep3[2];
+          }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < 9; ++k) pl[k] = sh.seq_buf[k];
+          __syncthreads();  // seq_buf is scratch again next iteration
+        } else {
+          double s5[5] = {0, 0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, o5[5], o4[4];
+          for (int i = tid; i < ns; i += nthr) {
+            if (match[i] == 0xffff) continue;
+            float v[9];
+            terms(i, v);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) s5[k] += (double)v[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s4[k] += (double)v[5 + k];
+          }
+          block_sum<5>(s5, sh.red, red_phase, o5);
+          block_sum<4>(s4, sh.red, red_phase, o4);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) pl[k] = (float)o5[k];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pl[5 + k] = (float)o4[k];
         }
-        __syncthreads();
-        mrx = sh.seq[0], mry = sh.seq[1], mfx = sh.seq[2], mfy = sh.seq[3];
-        __syncthreads();  // sh.seq is rewritten below
-      }
-      const float winv = __fdiv_rn(1.0f, (float)n_keep);
-      mrx = __fmul_rn(mrx, winv), mry = __fmul_rn(mry, winv);
-      mfx = __fmul_rn(mfx, winv), mfy = __fmul_rn(mfy, winv);
+      } else {
+        if (seq) {
+          // warp 0 forms the four sums (step x, step y, matched reference x, y); dropped pairs add +0
+          if (tid < 32) {
+            const float sum = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
+              const int m = match[i];
+              if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
+              const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+              const float2 r = sorted[m];
+              return make_float4(q.x, q.y, r.x, r.y);
+            });
+            if (tid < 4) sh.seq[tid] = sum;
+          }
+          __syncthreads();
+          mrx = sh.seq[0], mry = sh.seq[1], mfx = sh.seq[2], mfy = sh.seq[3];
+          __syncthreads();  // sh.seq is rewritten below
+        }
+        const float winv = __fdiv_rn(1.0f, (float)n_keep);
+        mrx = __fmul_rn(mrx, winv), mry = __fmul_rn(mry, winv);
+        mfx = __fmul_rn(mfx, winv), mfy = __fmul_rn(mfy, winv);
 
-      // 3d. cross-covariance of the centred pairs
-      double t4[4];
-      if (seq) {
-        if (tid < 32) {  // m00 = qx*px, m01 = qx*py, m10 = qy*px, m11 = qy*py
-          const float sum = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
-            const int m = match[i];
-            if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
+        // 3d. cross-covariance of the centred pairs
+        if (seq) {
+          if (tid < 32) {  // m00 = qx*px, m01 = qx*py, m10 = qy*px, m11 = qy*py
+            const float sum = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
+              const int m = match[i];
+              if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
+              const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+              const float2 r = sorted[m];
+              const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
+              const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
+              return make_float4(__fmul_rn(qx, px), __fmul_rn(qx, py), __fmul_rn(qy, px), __fmul_rn(qy, py));
+            });
+            if (tid < 4) sh.seq[tid] = sum;
+          }
+          __syncthreads();
+          t4[0] = (double)sh.seq[0], t4[1] = (double)sh.seq[1], t4[2] = (double)sh.seq[2], t4[3] = (double)sh.seq[3];
+        } else {
+          double s4[4] = {0, 0, 0, 0};
+          for (int i = tid; i < ns; i += nthr) {
+            if (match[i] == 0xffff) continue;
             const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-            const float2 r = sorted[m];
+            const float2 r = sorted[match[i]];
             const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
             const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
-            return make_float4(__fmul_rn(qx, px), __fmul_rn(qx, py), __fmul_rn(qy, px), __fmul_rn(qy, py));
-          });
-          if (tid < 4) sh.seq[tid] = sum;
+            s4[0] += (double)__fmul_rn(qx, px), s4[1] += (double)__fmul_rn(qx, py);
+            s4[2] += (double)__fmul_rn(qy, px), s4[3] += (double)__fmul_rn(qy, py);
+          }
+          block_sum<4>(s4, sh.red, red_phase, t4);
         }
-        __syncthreads();
-        t4[0] = (double)sh.seq[0], t4[1] = (double)sh.seq[1], t4[2] = (double)sh.seq[2], t4[3] = (double)sh.seq[3];
-      } else {
-        double s4[4] = {0, 0, 0, 0};
-        for (int i = tid; i < ns; i += nthr) {
-          if (match[i] == 0xffff) continue;
-          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-          const float2 r = sorted[match[i]];
-          const float px = __fsub_rn(q.x, mrx), py = __fsub_rn(q.y, mry);
-          const float qx = __fsub_rn(r.x, mfx), qy = __fsub_rn(r.y, mfy);
-          s4[0] += (double)__fmul_rn(qx, px), s4[1] += (double)__fmul_rn(qx, py);
-          s4[2] += (double)__fmul_rn(qy, px), s4[3] += (double)__fmul_rn(qy, py);
-        }
-        block_sum<4>(s4, sh.red, red_phase, t4);
       }
 
       // 3e. rigid fit, T_iter update, checkers (one thread)
       if (tid == 0) {
-        const float m00 = (float)t4[0], m01 = (float)t4[1], m10 = (float)t4[2], m11 = (float)t4[3];
-        const float a = __fadd_rn(m00, m11), bq = __fsub_rn(m10, m01);
-        const float h = sqrtf(__fadd_rn(__fmul_rn(a, a), __fmul_rn(bq, bq)));
-        float c = 1.f, s = 0.f;
-        if (h > 0.f) c = __fdiv_rn(a, h), s = __fdiv_rn(bq, h);
-        const float tx = __fsub_rn(mfx, __fadd_rn(__fmul_rn(c, mrx), __fmul_rn(-s, mry)));
-        const float ty = __fsub_rn(mfy, __fadd_rn(__fmul_rn(s, mrx), __fmul_rn(c, mry)));
+        float c = 1.f, s = 0.f, tx, ty;
+        if constexpr (PLANE) {
+          // A x = b by Cholesky (A.llt()); an unknown whose pivot is not positive stays 0
+          const float a00 = pl[0], a01 = pl[1], a02 = pl[2], a11 = pl[3], a12 = pl[4], a22 = pl[5];
+          const float b0 = -pl[6], b1 = -pl[7], b2 = -pl[8];
+          float l00 = 0.f, l10 = 0.f, l20 = 0.f, l11 = 0.f, l21 = 0.f, l22 = 0.f;
+          const bool p0 = a00 > 0.f;
+          if (p0) l00 = __fsqrt_rn(a00), l10 = __fdiv_rn(a01, l00), l20 = __fdiv_rn(a02, l00);
+          const float d1 = __fsub_rn(a11, __fmul_rn(l10, l10));
+          const bool p1 = d1 > 0.f;
+          if (p1) l11 = __fsqrt_rn(d1), l21 = __fdiv_rn(__fsub_rn(a12, __fmul_rn(l20, l10)), l11);
+          const float d2 = __fsub_rn(__fsub_rn(a22, __fmul_rn(l20, l20)), __fmul_rn(l21, l21));
+          const bool p2 = d2 > 0.f;
+          if (p2) l22 = __fsqrt_rn(d2);
+          const float y0 = p0 ? __fdiv_rn(b0, l00) : 0.f;
+          const float y1 = p1 ? __fdiv_rn(__fsub_rn(b1, __fmul_rn(l10, y0)), l11) : 0.f;
+          const float y2 = p2 ? __fdiv_rn(__fsub_rn(__fsub_rn(b2, __fmul_rn(l20, y0)), __fmul_rn(l21, y1)), l22) : 0.f;
+          const float x2 = p2 ? __fdiv_rn(y2, l22) : 0.f;
+          const float x1 = p1 ? __fdiv_rn(__fsub_rn(y1, __fmul_rn(l21, x2)), l11) : 0.f;
+          const float x0 = p0 ? __fdiv_rn(__fsub_rn(__fsub_rn(y0, __fmul_rn(l10, x1)), __fmul_rn(l20, x2)), l00) : 0.f;
+          c = (float)cos((double)x0), s = (float)sin((double)x0);  // Rotation2D(x0)
+          tx = x1, ty = x2;
+        } else {
+          const float m00 = (float)t4[0], m01 = (float)t4[1], m10 = (float)t4[2], m11 = (float)t4[3];
+          const float a = __fadd_rn(m00, m11), bq = __fsub_rn(m10, m01);
+          const float h = sqrtf(__fadd_rn(__fmul_rn(a, a), __fmul_rn(bq, bq)));
+          if (h > 0.f) c = __fdiv_rn(a, h), s = __fdiv_rn(bq, h);
+          tx = __fsub_rn(mfx, __fadd_rn(__fmul_rn(c, mrx), __fmul_rn(-s, mry)));
+          ty = __fsub_rn(mfy, __fadd_rn(__fmul_rn(s, mrx), __fmul_rn(c, mry)));
+        }
         const float dT[9] = {c, -s, tx, s, c, ty, 0.f, 0.f, 1.f};
         float Tn[9];
         mat3_mul_rn(dT, Ti, Tn);
@@ -1003,6 +1094,9 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   SFE_REQUIRE(nt_max <= 65535 && ns_max <= 65535, "icp: clouds of more than 65535 points are not supported (got %d, %d)",
               ns_max, nt_max);
   SFE_REQUIRE(prm->max_iterations >= 1, "icp: maxIterationCount must be >= 1");
+  SFE_REQUIRE(prm->minimizer == 0 || prm->minimizer == 1, "icp: unknown error minimizer %d", prm->minimizer);
+  SFE_REQUIRE(prm->minimizer == 0 || (prm->normals_knn >= 3 && prm->normals_knn <= GRID_KNN_MAX),
+              "icp: SurfaceNormalDataPointsFilter knn %d is not supported (3..%d)", prm->normals_knn, GRID_KNN_MAX);
   SFE_REQUIRE(prm->smooth_length < ICP_HIST, "icp: smoothLength %d is not supported (at most %d)", prm->smooth_length,
               ICP_HIST - 1);
   IcpBatch b{};
@@ -1054,17 +1148,22 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   // instantiation: (threads, register budget).  512-thread CTAs whose shared memory allows only one per SM get the
   // full 128 registers.
   const int variant = threads == 128 ? 0 : (threads == 256 ? 1 : (smem > 110 * 1024 ? 3 : 2));
-  const void *fn = variant == 0   ? (const void *)icp_kernel<128, 6>
-                   : variant == 1 ? (const void *)icp_kernel<256, 4>
-                   : variant == 2 ? (const void *)icp_kernel<512, 2>
-                                  : (const void *)icp_kernel<512, 1>;
+  const bool plane = prm->minimizer == 1;
+  const void *fn = plane ? (variant == 0   ? (const void *)icp_kernel<128, 6, true>
+                            : variant == 1 ? (const void *)icp_kernel<256, 4, true>
+                            : variant == 2 ? (const void *)icp_kernel<512, 2, true>
+                                           : (const void *)icp_kernel<512, 1, true>)
+                         : (variant == 0   ? (const void *)icp_kernel<128, 6, false>
+                            : variant == 1 ? (const void *)icp_kernel<256, 4, false>
+                            : variant == 2 ? (const void *)icp_kernel<512, 2, false>
+                                           : (const void *)icp_kernel<512, 1, false>);
   // the attribute / occupancy queries are cached in the context per (variant, smem): the front end calls this per
   // copy chunk
   {  // the attribute belongs to (function, device), not to a context: only ever raise it, process-wide
     static std::mutex mu;
-    static size_t attr[64][4] = {};
+    static size_t attr[64][8] = {};
     std::lock_guard<std::mutex> lock(mu);
-    size_t &cur = attr[ctx->device & 63][variant];
+    size_t &cur = attr[ctx->device & 63][variant + (plane ? 4 : 0)];
     if (smem > cur) {
       SFE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cur = smem;
@@ -1072,12 +1171,12 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   }
   int c_per_sm = 0;
   for (const auto &e : ctx->icp_occ)
-    if (e.per_sm > 0 && e.smem == smem && e.threads == threads && e.variant == variant) c_per_sm = e.per_sm;
+    if (e.per_sm > 0 && e.smem == smem && e.threads == threads && e.variant == variant + (plane ? 4 : 0)) c_per_sm = e.per_sm;
   if (c_per_sm == 0) {
     int q = 1;
     SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, threads, smem));
     c_per_sm = q < 1 ? 1 : q;
-    ctx->icp_occ[ctx->icp_occ_next] = {smem, threads, c_per_sm, variant};
+    ctx->icp_occ[ctx->icp_occ_next] = {smem, threads, c_per_sm, variant + (plane ? 4 : 0)};
     ctx->icp_occ_next = (ctx->icp_occ_next + 1) % 8;
   }
   const int per_sm = c_per_sm;
@@ -1086,9 +1185,11 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
   int slots = grid;
   if (per_sm == 1 && P > grid) b.slot_by_smid = 1, slots = ICP_SM_SLOTS, grid = P;  // one CTA per problem
   const size_t orig_bytes = ((size_t)slots * b.nt_max * sizeof(uint16_t) + 15) & ~size_t(15);
-  int rc = ensure(ctx, ctx->scratch[SCR_ICP], orig_bytes);
+  const size_t nrm_bytes = plane ? (size_t)slots * b.nt_max * sizeof(float2) : 0;
+  int rc = ensure(ctx, ctx->scratch[SCR_ICP], orig_bytes + nrm_bytes);
   if (rc != SFE_OK) return rc;
   b.orig_ws = (uint16_t *)ctx->scratch[SCR_ICP].ptr;
+  b.nrm_ws = plane ? (float2 *)((char *)ctx->scratch[SCR_ICP].ptr + orig_bytes) : nullptr;
   void *args[] = {(void *)&b};
   SFE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, ctx->stream));
   ctx->launches++;

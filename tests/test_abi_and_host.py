@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 8
     for n in names:
         assert hasattr(lib, n), f"libsonarfe.so does not export {n}"
-    assert lib.sfe_version() == 200
+    assert lib.sfe_version() == 201
 
 
 def test_no_cpu_fallback_context_creation_fails_loudly_without_gpu():

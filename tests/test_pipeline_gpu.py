@@ -13,7 +13,7 @@ def _pose(T):
     return np.array([T[0, 2], T[1, 2], np.arctan2(T[1, 0], T[0, 0])], np.float64)
 
 
-@pytest.mark.parametrize("mode", ["checkers", "fixed20"])
+@pytest.mark.parametrize("mode", ["checkers", "fixed20", "plane"])
 def test_frontend_host_call_equals_oracle_chain(gpu_ctx, mode):
     n = 14
     d = synth.make_trajectory_frames(n, seed=3)
@@ -21,6 +21,8 @@ def test_frontend_host_call_equals_oracle_chain(gpu_ctx, mode):
     geo = featx_ref.Geometry(30.0 / 512, 512, d["bearings"])
     maps = _lib.Maps(gpu_ctx, geo.map_x, geo.map_y, 512, 512, geo.width, geo.height)
     kw = dict(smooth_length=0, max_iterations=20) if mode == "fixed20" else {}
+    if mode == "plane":   # X1: point-to-plane minimiser (icp.yaml:18-19) inside the fused call
+        kw = dict(minimizer=1, normals_knn=5)
     fe = pipeline.FrontEnd(gpu_ctx, maps, max_frames=32, icp=_lib.IcpParams(**kw), min_points=30)
     got = fe.run_host(frames, poses, chunk_frames=5)
     clouds, want = pipeline_ref.run(frames, poses, geo, min_points=30, icp_params=orc.IcpParams(**kw))
