@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=256, help="frames per host->device copy chunk (e2e)")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--minimizer", default="point", choices=["point", "plane"],
+                    help="ICP error minimiser: point = the shipped PointToPointErrorMinimizer (icp.yaml:20); plane = the "
+                         "PointToPlaneErrorMinimizer icp.yaml:18-19 keeps commented out (normals: knn 5), both arms")
     ap.add_argument("--pairs", type=int, default=80000, help="config 5: size of the scan-match backlog (0: skip)")
     ap.add_argument("--pair-steps", type=int, default=2, help="config 5: timed steps (after one warm-up step)")
     ap.add_argument("--pair-chunks", type=int, default=8, help="config 5: pieces per shard in the pipelined scatter")
@@ -150,7 +153,7 @@ def _cpu_init(bearings):
     except Exception:  # noqa: BLE001
         pass
     _W["geo"] = _cpu_geometry(bearings)
-    _W["prm"] = orc.IcpParams(smooth_length=0, max_iterations=20)
+    _W["prm"] = orc.IcpParams(smooth_length=0, max_iterations=20, minimizer=_W.get("minimizer", 0))
 
 
 def _cpu_cloud(img):
@@ -205,6 +208,7 @@ def run_reference(args):
     import torch  # noqa: F401  (frame renderer)
     from sonar_slam_b200 import synth
     cores, reported = host_cores()
+    _W["minimizer"] = 1 if args.minimizer == "plane" else 0   # (inherited by the forked workers)
     n = max(16, min(8 * cores, 1024))
     d = synth.make_trajectory_frames(n, seed=0)
     frames, poses = d["frames"].numpy(), d["poses_odom"]
@@ -221,6 +225,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "config4-pipeline: bounded sample of the bag replay per step",
                        "frames_per_step": n, "image": [R, B], "icp_iterations": 20, "window": 3,
+                       "icp_minimizer": args.minimizer,
                        "timing": "median of the timed steps; every step is the full sample",
                        "step_seconds": [round(x, 4) for x in secs]},
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "cores_reported_by_os": reported,
@@ -308,7 +313,9 @@ def run_ours(args):
     fx.generate_map_xy(synth.Ping(0, None, 30.0 / R, R, d["bearings"]))
     ctx = ops.context(local)
     maps = _lib.Maps(ctx, fx.map_x, fx.map_y, R, B, fx.width, fx.height)
-    fe = pipeline.FrontEnd(ctx, maps, max_frames=F, tau=TAU_SOCA, icp=_lib.IcpParams(smooth_length=0, max_iterations=20))
+    mini = _W["minimizer"] = 1 if args.minimizer == "plane" else 0
+    fe = pipeline.FrontEnd(ctx, maps, max_frames=F, tau=TAU_SOCA,
+                           icp=_lib.IcpParams(smooth_length=0, max_iterations=20, minimizer=mini))
     host_frames_t = torch.empty((F, R, B), dtype=torch.uint8, pin_memory=True)
     host_frames_t.copy_(frames_dev)
     host_frames = host_frames_t.numpy()
@@ -369,13 +376,13 @@ def run_ours(args):
 
     # ---- config 3 (rank 0) and config 5 (all ranks): 2 000 x 20 000-point scan matches
     cfg3, cfg5 = None, None
-    prm20 = _lib.IcpParams(smooth_length=0, max_iterations=20)
+    prm20 = _lib.IcpParams(smooth_length=0, max_iterations=20, minimizer=mini)
     try:
         if rank == 0:
             P3 = 8 * torch.cuda.get_device_properties(local).multi_processor_count
             s3, t3, g3 = make_pair_backlog(P3, f"cuda:{local}", n_scenes=16)
             cfg3 = {"pairs": P3, "source_points": 2000, "target_points": 20000, "waves": 8}
-            for name, prm in (("fixed20", prm20), ("checkers", _lib.IcpParams())):
+            for name, prm in (("fixed20", prm20), ("checkers", _lib.IcpParams(minimizer=mini))):
                 for _ in range(2):
                     r3 = sdist.unpack_results(sdist._default_icp(s3, t3, g3, prm))
                 ts = []
@@ -453,6 +460,7 @@ def run_ours(args):
                                    "cloud -> voxel 0.5 m -> outlier(1.0 m, 5) -> keyframe cloud (x, -z) -> ICP 20 "
                                    "iterations vs 3-frame submap",
                        "frames_per_step_per_gpu": F, "image": [R, B], "image_dtype": "u8", "icp_iterations": 20,
+                       "icp_minimizer": args.minimizer,
                        "window": 3, "sharding": "frames by rank (every rank replays the same seeded bag), no data-path collective",
                        "l2": f"inputs larger than L2 ({F * R * B / 2**20:.0f} MiB of frames per step)",
                        "frames_matched_last_step": int(stats[0].item()),
