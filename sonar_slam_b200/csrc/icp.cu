@@ -27,6 +27,7 @@ constexpr int ICP_THREADS = 512;
 constexpr int ICP_HIST = 16;  // differential-checker history kept (>= smoothLength + 1)
 constexpr int ICP_COARSE = 8;            // fine cells per coarse cell edge
 constexpr int ICP_COARSE_WORDS = 96;     // bitmap words: cnx*cny <= 2048 + margin
+constexpr int ICP_PLANE_SCRATCH = 2 * 9 * 36;  // floats (seq_sum9_warp)
 constexpr float ICP_PRUNED = 3.0e38f;    // "finite, but farther than we needed to know"
 
 enum { ICP_OK = 0, ICP_NO_OUTLIER = 1, ICP_NO_POINT = 2, ICP_NAN_ROT = 3, ICP_NAN_TRANS = 4, ICP_NOT_RIGID = 5,
@@ -293,6 +294,49 @@ __device__ __forceinline__ float seq_sum4_warp(int n, float *scratch, F term4) {
   return s;  // lanes c, c + 4, c + 8, ... all hold the sum of component c
 }
 
+// Point-to-plane: the nine sequential sums of the normal equations in one pass.  Same scheme as seq_sum4_warp with
+// nine rows -- lanes 0..8 each add one component's 32 values per batch, in point order -- and the per-pair normal
+// (a gather from global memory, ~700 cycles) requested for eight batches at once so that its latency is paid once
+// per 256 points, not once per batch.  `scratch` = [2][9][36] floats.  term9(i, m, n, v): the nine terms of kept
+// pair i (match m, normal n).  Lane c (c < 9) returns the sum of component c.
+template <typename F>
+__device__ __forceinline__ float seq_sum9_warp(int n, float *scratch, const uint16_t *match, const float2 *nrm, F term9) {
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  int it = 0;
+  for (int chunk = 0; chunk < n; chunk += 256) {
+    int mm[8];
+    float2 nn[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = chunk + 32 * k + lane;
+      mm[k] = i < n ? match[i] : 0xffff;
+      nn[k] = mm[k] != 0xffff ? nrm[mm[k]] : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (chunk + 32 * k >= n) break;  // (warp-uniform)
+      float *buf = scratch + (it & 1) * (9 * 36);
+      ++it;
+      float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (mm[k] != 0xffff) term9(chunk + 32 * k + lane, mm[k], nn[k], v);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) buf[c * 36 + lane] = v[c];
+      __syncwarp();
+      if (lane < 9) {
+        const float4 *r = reinterpret_cast<const float4 *>(buf + lane * 36);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = r[j];
+          s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, a.x), a.y), a.z), a.w);
+        }
+      }
+      // (this buffer is rewritten two batches from now: every lane passes the next batch's __syncwarp first)
+    }
+  }
+  return s;
+}
+
 // One sequential sum over values in global memory, p[0], p[stride], ... (the reference cloud's mean, once per
 // problem): lane j holds term base + j and a shuffle hands term j to every lane, so all lanes carry the same
 // running sum; eight batches (256 terms) are requested at once and the next eight are in flight while these are
@@ -358,6 +402,13 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   // the lanes of a warp look at neighbouring cells (similar amounts of work, the same shared-memory lines); results
   // are stored by point index and the sums run in point order, so the order is invisible in the results
   uint16_t *order = reinterpret_cast<uint16_t *>(smem_raw + off);
+  if (b.use_order) off += sizeof(uint16_t) * (size_t)b.ns_max;
+  off = (off + 15) & ~size_t(15);
+  // PLANE only: [2][9][36] floats for seq_sum9_warp.  dist[] is dead between the weights (3c) and the next
+  // iteration's search, which rewrites all of it: big problems (no byte of shared memory to spare at 2 000 x 20 000
+  // points) park the scratch there, small ones get their own 2.6 KB.
+  float *pl_scratch = b.ns_max >= ICP_PLANE_SCRATCH ? dist : reinterpret_cast<float *>(smem_raw + off);
+  (void)pl_scratch;
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   int red_phase = 0, tot_phase = 0, sel_pass = 0;  // rotation counters of the one-barrier reductions (CTA-uniform)
@@ -814,20 +865,18 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
           v[8] = __fmul_rn(n.y, dp);
         };
         if (seq) {
-          if (tid < 32) {  // three passes of four sequential sums; dropped pairs add +0
-            float keep3[3];
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              keep3[pass] = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
-                if (match[i] == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
-                float v[9];
-                terms(i, v);
-                return pass == 0 ? make_float4(v[0], v[1], v[2], v[3])
-                                 : (pass == 1 ? make_float4(v[4], v[5], v[6], v[7]) : make_float4(v[8], 0.f, 0.f, 0.f));
-              });
-              __syncwarp();
-            }
-            if (tid < 4) sh.seq_buf[tid] = keep3[0], sh.seq_buf[4 + tid] = keep3[1], sh.seq_buf[8 + tid] = keep3[2];
+          if (tid < 32) {  // nine sequential sums in one pass; dropped pairs add +0
+            const float sum = seq_sum9_warp(ns, pl_scratch, match, nrm, [&](int i, int m, float2 n, float (&v)[9]) {
+              const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+              const float2 r = sorted[m];
+              const float cr = __fsub_rn(__fmul_rn(q.x, n.y), __fmul_rn(q.y, n.x));
+              const float dp = __fadd_rn(__fmul_rn(__fsub_rn(q.x, r.x), n.x), __fmul_rn(__fsub_rn(q.y, r.y), n.y));
+              v[0] = __fmul_rn(cr, cr), v[1] = __fmul_rn(cr, n.x), v[2] = __fmul_rn(cr, n.y), v[3] = __fmul_rn(n.x, n.x);
+              v[4] = __fmul_rn(n.x, n.y), v[5] = __fmul_rn(n.y, n.y), v[6] = __fmul_rn(cr, dp), v[7] = __fmul_rn(n.x, dp);
+              v[8] = __fmul_rn(n.y, dp);
+            });
+            __syncwarp();
+            if (tid < 9) sh.seq_buf[tid] = sum;
           }
           __syncthreads();
 #pragma unroll
@@ -1130,7 +1179,8 @@ int icp_run(sfe_ctx *ctx, const sfe_icp_params *prm, const float *src_pts, const
     return ((sizeof(IcpShared) + 15) & ~size_t(15)) + sizeof(float2) * (size_t)b.nt_max +
            sizeof(uint32_t) * (size_t)((max_cells + 2) / 2 + 1) + 8 + sizeof(float2) * (size_t)b.ns_max +
            sizeof(float) * (size_t)b.ns_max + 2 * sizeof(uint16_t) * (size_t)b.ns_max + (size_t)b.ns_max + 4 +
-           sizeof(float) * (size_t)b.ns_max + (b.use_order ? sizeof(uint16_t) * (size_t)b.ns_max : 0) + 16;
+           sizeof(float) * (size_t)b.ns_max + (b.use_order ? sizeof(uint16_t) * (size_t)b.ns_max : 0) + 16 +
+           (prm->minimizer == 1 && b.ns_max < ICP_PLANE_SCRATCH ? 16 + ICP_PLANE_SCRATCH * sizeof(float) : 0);
   };
   // big problems: trade cell-table entries (coarser cells) for room before giving up
   while (smem_for(b.max_cells) > (size_t)ctx->max_smem_optin && b.max_cells > b.nt_max / 4 + 256)
