@@ -484,27 +484,29 @@ __device__ __forceinline__ NNResult nn_query_seeded(const GridView &g, float qx,
 // around its cell until the k-th distance is below the bound of everything outside the rings scanned; then mean,
 // 2x2 covariance and the unit eigenvector of the smaller eigenvalue in closed form -- every operation a float32
 // IEEE operation in the oracle's order, so the normals are bit-identical to the oracle's.
+// The running best-knn list is the caller's: bd[j * stride], bi[j * stride], j < knn.  The scan matcher hands out
+// shared memory that is idle while the normals are computed (stride = CTA size, one column per thread): a list in
+// local memory would spill past the little L1 that a CTA's shared-memory carve-out leaves (measured: 1.07 -> see
+// profiles/README.md), so local arrays (stride 1) are only the fallback for CTAs without that room.
 constexpr int GRID_KNN_MAX = 16;
-__device__ inline float2 grid_surface_normal(const GridView &g, int p, int knn) {
+__device__ inline float2 grid_surface_normal(const GridView &g, int p, int knn, float *bd, uint16_t *bi, int stride) {
   const float2 q = g.pts[p];
   const int cx = grid_cell_coord(q.x, g.ox, g.inv_cell, g.nx), cy = grid_cell_coord(q.y, g.oy, g.inv_cell, g.ny);
-  float bd[GRID_KNN_MAX];
-  int bi[GRID_KNN_MAX];
   int k = 0;
+  float kth = INFINITY;
   auto offer = [&](int s, int e) {
     for (int j = s; j < e; ++j) {
       const float2 t = g.pts[j];
       const float d2 = dist2_rn(q.x - t.x, q.y - t.y);
-      if (k == knn) {
-        if (d2 > bd[k - 1]) continue;
-        if (d2 == bd[k - 1] && g.orig[j] > g.orig[bi[k - 1]]) continue;
-      }
+      if (d2 > kth) continue;  // kth = the knn-th distance so far (+inf until knn points are listed)
+      if (d2 == kth && g.orig[j] > g.orig[bi[(k - 1) * stride]]) continue;
       int at = k < knn ? k++ : knn - 1;
-      while (at > 0 && (d2 < bd[at - 1] || (d2 == bd[at - 1] && g.orig[j] < g.orig[bi[at - 1]]))) {
-        bd[at] = bd[at - 1], bi[at] = bi[at - 1];
+      while (at > 0 && (d2 < bd[(at - 1) * stride] || (d2 == bd[(at - 1) * stride] && g.orig[j] < g.orig[bi[(at - 1) * stride]]))) {
+        bd[at * stride] = bd[(at - 1) * stride], bi[at * stride] = bi[(at - 1) * stride];
         --at;
       }
-      bd[at] = d2, bi[at] = j;
+      bd[at * stride] = d2, bi[at * stride] = (uint16_t)j;
+      if (k == knn) kth = bd[(k - 1) * stride];
     }
   };
   for (int kr = 0;; ++kr) {
@@ -519,14 +521,14 @@ __device__ inline float2 grid_surface_normal(const GridView &g, int p, int knn) 
       }
     }
     const float b2 = nn_block_bound2(g, q.x, q.y, cx, cy, kr);
-    if (b2 == INFINITY || (k == knn && bd[k - 1] < b2)) break;
+    if (b2 == INFINITY || kth < b2) break;
   }
   float sx = 0.f, sy = 0.f;
-  for (int j = 0; j < k; ++j) sx = __fadd_rn(sx, g.pts[bi[j]].x), sy = __fadd_rn(sy, g.pts[bi[j]].y);
+  for (int j = 0; j < k; ++j) sx = __fadd_rn(sx, g.pts[bi[j * stride]].x), sy = __fadd_rn(sy, g.pts[bi[j * stride]].y);
   const float kf = (float)k, mx = __fdiv_rn(sx, kf), my = __fdiv_rn(sy, kf);
   float a = 0.f, b = 0.f, c = 0.f;
   for (int j = 0; j < k; ++j) {
-    const float ux = __fsub_rn(g.pts[bi[j]].x, mx), uy = __fsub_rn(g.pts[bi[j]].y, my);
+    const float ux = __fsub_rn(g.pts[bi[j * stride]].x, mx), uy = __fsub_rn(g.pts[bi[j * stride]].y, my);
     a = __fadd_rn(a, __fmul_rn(ux, ux)), b = __fadd_rn(b, __fmul_rn(ux, uy)), c = __fadd_rn(c, __fmul_rn(uy, uy));
   }
   a = __fdiv_rn(a, kf), b = __fdiv_rn(b, kf), c = __fdiv_rn(c, kf);

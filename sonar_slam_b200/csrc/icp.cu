@@ -537,8 +537,19 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
     if constexpr (PLANE) {
       nrm = b.nrm_ws + (size_t)slot * b.nt_max;
       const int knn = min(max(prm.normals_knn, 1), GRID_KNN_MAX);
-      for (int j = tid; j < nt; j += nthr) nrm[j] = grid_surface_normal(g, j, knn);
-      // (published to the CTA by the barriers of step 2)
+      // best-knn list per thread: the per-source arrays (reading .. slack) are idle until step 2
+      unsigned char *scr = reinterpret_cast<unsigned char *>(reading);
+      const size_t scr_bytes = (size_t)(reinterpret_cast<unsigned char *>(slack + b.ns_max) - scr);
+      if (scr_bytes >= (size_t)nthr * knn * 6) {
+        float *bd = reinterpret_cast<float *>(scr) + tid;
+        uint16_t *bi = reinterpret_cast<uint16_t *>(scr + sizeof(float) * (size_t)nthr * knn) + tid;
+        for (int j = tid; j < nt; j += nthr) nrm[j] = grid_surface_normal(g, j, knn, bd, bi, nthr);
+      } else {
+        float bd[GRID_KNN_MAX];
+        uint16_t bi[GRID_KNN_MAX];
+        for (int j = tid; j < nt; j += nthr) nrm[j] = grid_surface_normal(g, j, knn, bd, bi, 1);
+      }
+      // (published to the CTA, and the scratch released, by the barriers of step 2)
     }
 
     // ---- 2. reading into the centred frame; T_iter = I; checker history

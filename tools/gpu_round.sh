@@ -33,6 +33,8 @@ for s in $steps; do
                 python tools/prof_icp.py 296 > gpurun_out/${tag}_ncu_icp.log 2>&1; tail -2 gpurun_out/${tag}_ncu_icp.log ;;
     ncu_pipe) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"icp_kernel|feat|cart_|downsample|outlier|assemble" -s 14 -c 7 -f -o gpurun_out/${tag}_prof_pipeline \
                 python tools/prof_pipeline.py 1024 > gpurun_out/${tag}_ncu_pipe.log 2>&1; tail -2 gpurun_out/${tag}_ncu_pipe.log ;;
+    ncu_plane) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"icp_kernel" -s 4 -c 2 -f -o gpurun_out/${tag}_prof_plane \
+                python tools/prof_pipeline.py 1024 1 > gpurun_out/${tag}_ncu_plane.log 2>&1; tail -2 gpurun_out/${tag}_ncu_plane.log ;;
     n2)       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 \
                 > gpurun_out/${tag}_bench_n2.json 2> gpurun_out/${tag}_bench_n2.err; tail -c 2500 gpurun_out/${tag}_bench_n2.json; tail -5 gpurun_out/${tag}_bench_n2.err ;;
     n8)       NCCL_DEBUG=INFO timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 \
