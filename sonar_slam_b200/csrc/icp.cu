@@ -27,7 +27,7 @@ constexpr int ICP_THREADS = 512;
 constexpr int ICP_HIST = 16;  // differential-checker history kept (>= smoothLength + 1)
 constexpr int ICP_COARSE = 8;            // fine cells per coarse cell edge
 constexpr int ICP_COARSE_WORDS = 96;     // bitmap words: cnx*cny <= 2048 + margin
-constexpr int ICP_PLANE_SCRATCH = 2 * 9 * 36;  // floats (seq_sum9_warp)
+constexpr int ICP_PLANE_SCRATCH = 2 * 320;  // floats (seq_sum9_warp: two buffers of 9 rows, 36 apart, 32 used)
 constexpr float ICP_PRUNED = 3.0e38f;    // "finite, but farther than we needed to know"
 
 enum { ICP_OK = 0, ICP_NO_OUTLIER = 1, ICP_NO_POINT = 2, ICP_NAN_ROT = 3, ICP_NAN_TRANS = 4, ICP_NOT_RIGID = 5,
@@ -297,7 +297,7 @@ __device__ __forceinline__ float seq_sum4_warp(int n, float *scratch, F term4) {
 // Point-to-plane: the nine sequential sums of the normal equations in one pass.  Same scheme as seq_sum4_warp with
 // nine rows -- lanes 0..8 each add one component's 32 values per batch, in point order -- and the per-pair normal
 // (a gather from global memory, ~700 cycles) requested for eight batches at once so that its latency is paid once
-// per 256 points, not once per batch.  `scratch` = [2][9][36] floats.  term9(i, m, n, v): the nine terms of kept
+// per 256 points, not once per batch.  `scratch` = 2 x 320 floats (nine rows 36 floats apart, 32 used).  term9(i, m, n, v): the nine terms of kept
 // pair i (match m, normal n).  Lane c (c < 9) returns the sum of component c.
 template <typename F>
 __device__ __forceinline__ float seq_sum9_warp(int n, float *scratch, const uint16_t *match, const float2 *nrm, F term9) {
@@ -316,19 +316,19 @@ __device__ __forceinline__ float seq_sum9_warp(int n, float *scratch, const uint
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (chunk + 32 * k >= n) break;  // (warp-uniform)
-      float *buf = scratch + (it & 1) * (9 * 36);
+      float *buf = scratch + (it & 1) * 320;
       ++it;
       float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (mm[k] != 0xffff) term9(chunk + 32 * k + lane, mm[k], nn[k], v);
 #pragma unroll
       for (int c = 0; c < 9; ++c) buf[c * 36 + lane] = v[c];
       __syncwarp();
-      if (lane < 9) {
-        const float4 *r = reinterpret_cast<const float4 *>(buf + lane * 36);
+      if (lane < 9) {  // (8-byte loads: the scratch may sit on dist[], which is only 8-byte aligned)
+        const float2 *r = reinterpret_cast<const float2 *>(buf + lane * 36);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 a = r[j];
-          s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, a.x), a.y), a.z), a.w);
+        for (int j = 0; j < 16; ++j) {
+          const float2 a = r[j];
+          s = __fadd_rn(__fadd_rn(s, a.x), a.y);
         }
       }
       // (this buffer is rewritten two batches from now: every lane passes the next batch's __syncwarp first)
@@ -404,9 +404,10 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
   uint16_t *order = reinterpret_cast<uint16_t *>(smem_raw + off);
   if (b.use_order) off += sizeof(uint16_t) * (size_t)b.ns_max;
   off = (off + 15) & ~size_t(15);
-  // PLANE only: [2][9][36] floats for seq_sum9_warp.  dist[] is dead between the weights (3c) and the next
-  // iteration's search, which rewrites all of it: big problems (no byte of shared memory to spare at 2 000 x 20 000
-  // points) park the scratch there, small ones get their own 2.6 KB.
+  // PLANE only: 640 floats for seq_sum9_warp.  dist[] is dead between the weights (3c) and the next iteration's
+  // search, which rewrites all of it: launches with room for 640 source points (the front end's small class is
+  // exactly that, and sized to six CTAs per SM to the byte; 2 000 x 20 000 points leave nothing to spare at all)
+  // park the scratch there, smaller ones get their own 2.5 KB.
   float *pl_scratch = b.ns_max >= ICP_PLANE_SCRATCH ? dist : reinterpret_cast<float *>(smem_raw + off);
   (void)pl_scratch;
 

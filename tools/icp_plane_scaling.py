@@ -25,10 +25,10 @@ small, gsm = [], []
 for s in range(64):
     a, b, T = synth.make_icp_pair(5000 + s, n_source=int(rng.integers(300, 420)), n_target=int(rng.integers(900, 1100)))
     small.append((a, b)); gsm.append(T @ synth.se2(*rng.normal(0, [0.1, 0.1, 0.01])))
-for name, pairs, P, ns, nt, g in (("2k/20k x148", big, 148, 2000, 20000, None), ("360/1000 x4096", small, 4096, 420, 1100, gsm)):
+for name, pairs, P, ns, nt, g in (("2k/20k x148", big, 148, 2000, 20000, None), ("360/1000 x4096", small, 4096, 640, 1100, gsm)):
     a = pack(pairs, P)
     gs = torch.eye(3, device="cuda").repeat(P, 1, 1).contiguous() if g is None else \
         torch.from_numpy(np.stack([g[i % len(g)] for i in range(P)]).astype(np.float32)).cuda()
-    for mini in (0, 1):
-        print(name, "minimizer", mini, {it: round(t(a, gs, _lib.IcpParams(smooth_length=0, max_iterations=it, minimizer=mini), ns, nt), 3)
+    for mini, fl in ((0, 0), (1, 0)):
+        print(name, "minimizer", mini, fl, {it: round(t(a, gs, _lib.IcpParams(smooth_length=0, max_iterations=it, minimizer=mini, flags=fl), ns, nt), 3)
                                         for it in (1, 2, 5, 10, 20)})
