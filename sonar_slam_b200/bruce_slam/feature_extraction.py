@@ -134,8 +134,12 @@ class FeatureExtraction(object):
         return self._maps
 
     def publish_features(self, ping, points):
-        """The reference publishes a PointCloud2 here (:175-193); we keep the cloud."""
+        """The reference publishes a PointCloud2 here (:175-193).  The cloud is kept and returned as before; the
+        message itself (same bytes, no ROS: bruce_slam/conversions.py) is left in `self.feature_msg` for a caller
+        that forwards it."""
         self.points = points
+        from . import conversions
+        self.feature_msg = conversions.feature_msg(ping, points)
         return points
 
     def ping_image(self, sonar_msg):

@@ -5,6 +5,7 @@ import torch
 
 from oracle import featx_ref, oracle as orc, pipeline_ref
 from sonar_slam_b200 import _lib, pipeline, synth
+from sonar_slam_b200.bruce_slam import conversions
 
 pytestmark = pytest.mark.gpu
 
@@ -105,8 +106,10 @@ def test_frontend_equals_node_chain_with_slam_sign_convention(gpu_ctx, icp_yaml)
     for i in range(n):
         ping = synth.Ping(ping_id=i, image=frames[i], range_resolution=30.0 / 512, num_ranges=512, bearings=d["bearings"])
         pts = fx.callback(ping)                                            # feature node
-        xyz = np.c_[pts[:, 0], np.zeros(len(pts)), pts[:, 1]].astype(np.float32)   # feature_extraction.py:182 (float32 msg)
-        points = np.c_[xyz[:, 0], -1 * xyz[:, 2]]                          # slam_ros.py:169-170
+        # the hand-off as the nodes do it: PointCloud2 [p0, 0, p1] (feature_extraction.py:181-190, float32 on the
+        # wire) read back as (x, -z) (slam_ros.py:169-170) -- bruce_slam/conversions.py, same bytes without ROS
+        points = conversions.keyframe_points(fx.feature_msg)
+        assert fx.feature_msg.width == len(pts) and fx.feature_msg.point_step == 12
         slam.keyframes.append(KF(points, Pose2(*poses[i])))
         if i == 0:
             edges.append(None)
