@@ -6,6 +6,7 @@ tag=$1; rnd=${2:-r02}
 cd "$(dirname "$0")/.."
 G=gpurun_out; P=profiles
 [ -f $G/${tag}_bench.json ] && grep '^{' $G/${tag}_bench.json | tail -1 > $P/${rnd}_bench_n1.json
+[ -f $G/${tag}_bench_plane.json ] && grep '^{' $G/${tag}_bench_plane.json | tail -1 > $P/${rnd}_bench_n1_plane.json
 [ -f $G/${tag}_bench_ref.json ] && grep '^{' $G/${tag}_bench_ref.json | tail -1 > $P/${rnd}_bench_reference_arm.json
 for n in 2 4 8; do f=$(ls $G/*_bench_n$n.json 2>/dev/null | tail -1); [ -n "$f" ] && grep '^{' $f | tail -1 > $P/${rnd}_bench_n$n.json; done
 [ -f $G/icp_parity_sweep.json ] && cp $G/icp_parity_sweep.json $P/${rnd}_icp_parity_sweep.json
@@ -22,6 +23,7 @@ if [ -f $G/${tag}_prof_pipeline.ncu-rep ]; then
   args="$args pipeline_remove_outlier=$G/${tag}_prof_pipeline.ncu-rep@remove_outlier"
   args="$args pipeline_icp_128=$G/${tag}_prof_pipeline.ncu-rep@icp_kernel<128"
 fi
+[ -f $G/${tag}_prof_plane.ncu-rep ] && args="$args pipeline_icp_128_plane=$G/${tag}_prof_plane.ncu-rep@icp_kernel<128"
 [ -n "$args" ] && python tools/ncu_summary.py $P/${rnd}_ncu_full_summaries.json $args
 {
   echo "# hot source lines (ncu --set full --import-source on; tools/ncu_hot_lines.py) -- round $rnd, gpurun tag $tag"
@@ -32,6 +34,7 @@ fi
     python tools/ncu_hot_lines.py $G/${tag}_prof_pipeline.ncu-rep "downsample#2" sonar_slam_b200/libsonarfe.so 14
     python tools/ncu_hot_lines.py $G/${tag}_prof_pipeline.ncu-rep "icp_kernel<(int)128" sonar_slam_b200/libsonarfe.so 20
   fi
+  [ -f $G/${tag}_prof_plane.ncu-rep ] && python tools/ncu_hot_lines.py $G/${tag}_prof_plane.ncu-rep "icp_kernel<(int)128" sonar_slam_b200/libsonarfe.so 14
 } > $P/${rnd}_hot_lines.txt 2>&1 || true
 # SASS excerpt: the interior 16-row block of the pipeline's CFAR kernel + the TMA / mbarrier instructions of the library
 {
