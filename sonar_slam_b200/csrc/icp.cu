@@ -23,6 +23,9 @@
 
 namespace sfe {
 
+#ifndef SFE_SEQ_PIPE_MIN
+#define SFE_SEQ_PIPE_MIN 256  // CTA sizes from which the sequential sums are software-pipelined (register budget)
+#endif
 constexpr int ICP_THREADS = 512;
 constexpr int ICP_HIST = 16;  // differential-checker history kept (>= smoothLength + 1)
 constexpr int ICP_COARSE = 8;            // fine cells per coarse cell edge
@@ -916,7 +919,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         if (seq) {
           // warp 0 forms the four sums (step x, step y, matched reference x, y); dropped pairs add +0
           if (tid < 32) {
-            const float sum = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
+            const float sum = seq_sum4_warp<(THREADS >= SFE_SEQ_PIPE_MIN)>(ns, sh.seq_buf, [&](int i) -> float4 {
               const int m = match[i];
               if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
               const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
@@ -936,7 +939,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         // 3d. cross-covariance of the centred pairs
         if (seq) {
           if (tid < 32) {  // m00 = qx*px, m01 = qx*py, m10 = qy*px, m11 = qy*py
-            const float sum = seq_sum4_warp<(THREADS >= 256)>(ns, sh.seq_buf, [&](int i) -> float4 {
+            const float sum = seq_sum4_warp<(THREADS >= SFE_SEQ_PIPE_MIN)>(ns, sh.seq_buf, [&](int i) -> float4 {
               const int m = match[i];
               if (m == 0xffff) return make_float4(0.f, 0.f, 0.f, 0.f);
               const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
