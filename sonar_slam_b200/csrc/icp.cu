@@ -567,6 +567,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       sh.ht_x[0] = 0.f, sh.ht_y[0] = 0.f;
       sh.hn = 1;
       sh.iterate = 1;
+      sh.sel_val = 0;  // (also the one-pass path's list counter, see 3a)
     }
     __syncthreads();
     for (int i = tid; i < ns; i += nthr) {
@@ -653,24 +654,83 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
       // certificate size: a few of the point's steps (steps shrink as the scan converges), a fraction of a cell at most
       auto margin_for = [&](float step) { return fminf(fmaxf(b.margin_mult * step, 0.01f * g.cell), 0.35f * g.cell); };
       if (small) {
-        for (int ii = tid; ii < ns; ii += nthr) {
-          const int i = b.use_order ? order[ii] : ii;
-          const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
-          const int seed = prev[i];
-          NNResult r;
-          float d2s, step, lb2;
-          if (seed == 0xffff) {
-            r = nn_query_certified(g, q.x, q.y, max_d2, &lb2);
-            certify(i, lb2);
-          } else if (certified(i, q, seed, d2s, step)) {
-            r.d2 = d2s, r.pos = seed, r.tie = 0;
-          } else {
-            r = nn_query_seeded_certified(g, q.x, q.y, max_d2, seed, margin_for(step), &lb2);
-            certify(i, lb2);
+        if constexpr (THREADS <= 256) {
+          // Two halves, so that the lanes of a warp stay on one code path.  First every point tests its certificate
+          // (one distance; points without a seed search at once: that is the first iteration, all lanes together);
+          // the points whose certificate failed are only LISTED -- in match[], which is rewritten below anyway, with
+          // the counter in sel_val (zeroed by the single-thread step of the previous iteration).  Then the list is
+          // searched densely.  In one loop the re-search ran with 2.4 of 32 lanes active and took 25 % of this
+          // kernel's warp instructions on the front end's problems (tools/ncu_call_sites.py).
+          uint16_t *todo = match;
+          for (int base = 0; base < ns; base += nthr) {
+            const int ii = base + tid;
+            bool later = false;
+            int i = 0;
+            if (ii < ns) {
+              i = b.use_order ? order[ii] : ii;
+              const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+              const int seed = prev[i];
+              float d2s, step, lb2;
+              if (seed == 0xffff) {
+                const NNResult r = nn_query_certified(g, q.x, q.y, max_d2, &lb2);
+                certify(i, lb2);
+                dist[i] = r.d2;
+                prev[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
+                n_fin += r.pos >= 0;
+              } else if (certified(i, q, seed, d2s, step)) {
+                dist[i] = d2s;  // prev[i] stays
+                n_fin += 1;
+              } else {
+                later = true;
+              }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, later);
+            if (m) {  // one shared-memory atomic per warp
+              const int lane = tid & 31, lead = __ffs(m) - 1;
+              int at = 0;
+              if (lane == lead) at = (int)atomicAdd(&sh.sel_val, (uint32_t)__popc(m));
+              at = __shfl_sync(0xffffffffu, at, lead);
+              if (later) todo[at + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+            }
           }
-          dist[i] = r.d2;
-          match[i] = prev[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
-          n_fin += r.pos >= 0;
+          __syncthreads();
+          const int n_todo = (int)sh.sel_val;
+          for (int k = tid; k < n_todo; k += nthr) {
+            const int i = todo[k];
+            const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+            const float2 qo = apply_T(Tp, reading[i].x, reading[i].y);
+            const float step = sqrtf(dist2_rn(q.x - qo.x, q.y - qo.y));
+            float lb2;
+            const NNResult r = nn_query_seeded_certified(g, q.x, q.y, max_d2, prev[i], margin_for(step), &lb2);
+            certify(i, lb2);
+            dist[i] = r.d2;
+            prev[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
+            n_fin += r.pos >= 0;
+          }
+          __syncthreads();
+          for (int i = tid; i < ns; i += nthr) match[i] = prev[i];
+        } else {
+          // (512-thread CTAs rarely see a problem this small: the single loop is kept there, and with it the code of the
+          //  config-3 instantiation)
+          for (int ii = tid; ii < ns; ii += nthr) {
+            const int i = b.use_order ? order[ii] : ii;
+            const float2 q = apply_T(Ti, reading[i].x, reading[i].y);
+            const int seed = prev[i];
+            NNResult r;
+            float d2s, step, lb2;
+            if (seed == 0xffff) {
+              r = nn_query_certified(g, q.x, q.y, max_d2, &lb2);
+              certify(i, lb2);
+            } else if (certified(i, q, seed, d2s, step)) {
+              r.d2 = d2s, r.pos = seed, r.tie = 0;
+            } else {
+              r = nn_query_seeded_certified(g, q.x, q.y, max_d2, seed, margin_for(step), &lb2);
+              certify(i, lb2);
+            }
+            dist[i] = r.d2;
+            match[i] = prev[i] = r.pos >= 0 ? (uint16_t)r.pos : (uint16_t)0xffff;
+            n_fin += r.pos >= 0;
+          }
         }
       }
       const float stop_a = (0.999f * g.cell) * (0.999f * g.cell);
@@ -1004,6 +1064,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kernel(const IcpBatch b) {
         mat3_mul_rn(dT, Ti, Tn);
 #pragma unroll
         for (int i = 0; i < 9; ++i) sh.Tprev[i] = Ti[i], sh.Ti[i] = Tn[i];
+        sh.sel_val = 0;  // the next iteration's list counter (the select that also uses it is done)
         sh.inliers = n_keep;
         const int count = ++sh.count;
         bool counter_stop = false;
