@@ -43,3 +43,21 @@ def test_bench_refuses_to_run_the_product_path_without_a_gpu():
         return
     r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "0"], capture_output=True, text=True)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_clock_sampler_keeps_the_load_until_samples_arrive(tmp_path, monkeypatch):
+    """nvidia-smi that starts slower than the timed region (eight of them at N = 8): the sampler keeps the workload
+    running, untimed, until it has its samples instead of reporting none."""
+    import stat
+    import time
+    import bench
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.4\nwhile true; do echo '0, 1965, 1965, 700.0, Not Active, Not Active, "
+                    "Not Active, Active'; sleep 0.05; done\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{tmp_path}:" + __import__("os").environ["PATH"])
+    c = bench.ClockSampler(0)
+    c.start()
+    extra = c.keep_load_until(3, lambda: time.sleep(0.01))
+    out = c.stop()
+    assert extra > 0 and out["samples"] >= 3 and out["sm_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
