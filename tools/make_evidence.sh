@@ -8,7 +8,7 @@ G=gpurun_out; P=profiles
 [ -f $G/${tag}_bench.json ] && grep '^{' $G/${tag}_bench.json | tail -1 > $P/${rnd}_bench_n1.json
 [ -f $G/${tag}_bench_plane.json ] && grep '^{' $G/${tag}_bench_plane.json | tail -1 > $P/${rnd}_bench_n1_plane.json
 [ -f $G/${tag}_bench_ref.json ] && grep '^{' $G/${tag}_bench_ref.json | tail -1 > $P/${rnd}_bench_reference_arm.json
-for n in 2 4 8; do f=$(ls $G/*_bench_n$n.json 2>/dev/null | tail -1); [ -n "$f" ] && grep '^{' $f | tail -1 > $P/${rnd}_bench_n$n.json; done
+for n in 2 4 8; do f=$G/${tag}_bench_n$n.json; [ -f "$f" ] || f=$(ls -t $G/*_bench_n$n.json 2>/dev/null | head -1); [ -n "$f" ] && [ -f "$f" ] && grep '^{' $f | tail -1 > $P/${rnd}_bench_n$n.json; done
 [ -f $G/icp_parity_sweep.json ] && cp $G/icp_parity_sweep.json $P/${rnd}_icp_parity_sweep.json
 [ -f $G/${tag}_launches.csv ] && cp $G/${tag}_launches.csv $P/${rnd}_launch_list_ncu.csv && \
   python tools/launch_summary.py $P/${rnd}_launch_list_ncu.csv $P/${rnd}_launch_list_summary.csv 2 28 > /dev/null
