@@ -169,7 +169,7 @@ void orc_match_brute(const float *ref, int n_ref, const float *in, int n_in, flo
 int orc_remove_outlier(const float *pts, int n, int dim, double radius, int min_points, uint8_t *keep) {
   const double r2 = radius * radius;
   /* grid over x,y with cell = radius for the neighbour scan (exact: all candidates are re-tested) */
-  float *xy = (float *)malloc(sizeof(float) * 2 * (size_t)(n > 0 ? n : 1));
+  float *xy = (float *)calloc(2 * (size_t)(n > 0 ? n : 1), sizeof(float));
   for (int i = 0; i < n; ++i) xy[2 * i] = pts[(size_t)i * dim], xy[2 * i + 1] = pts[(size_t)i * dim + 1];
   nn_grid *g = nn_grid_build(xy, n);
   int kept = 0;
