@@ -4,7 +4,8 @@ The per-keyframe path is embarrassingly parallel given the odometry poses (SURVE
 coupling between neighbouring frames is the scan-matching window (frame i is matched against frames
 i-window .. i-1), so every shard carries `window` halo frames in front of it whose clouds are recomputed
 locally and whose results are dropped.  torch.distributed (NCCL on GPUs, gloo on CPU for tests) is used
-only at the edges: scatter the backlog from rank 0, gather the 64-byte-per-frame results.
+only at the edges: scatter the backlog from rank 0 (send / recv), gather the per-frame results (one tensor gather
+per result field).
 """
 import numpy as np
 import torch
@@ -59,17 +60,30 @@ def scatter_backlog(frames, poses, window, device="cpu", src=0):
     return f_local, p_local, s - h
 
 
-def gather_results(local, n_halo, n_total, dst=0):
+def gather_results(local, n_halo, n_total, dst=0, device=None):
     """local: dict of per-frame numpy arrays for the rank's [halo_start, end) frames.  Rank `dst` gets the
     concatenation over ranks in frame order with halos removed (others get None).  The first frame of
-    every shard but the first keeps its halo-informed result; frame 0 of the backlog stays "skipped"."""
+    every shard but the first keeps its halo-informed result; frame 0 of the backlog stays "skipped".
+
+    One `dist.gather` of a tensor per key (NCCL on GPUs, gloo in the CPU tests; no pickling): every rank knows every
+    shard's length from `shard_bounds(n_total, world)`, shards are padded to the longest one for the collective."""
     rank, world = dist.get_rank(), dist.get_world_size()
-    own = {k: np.ascontiguousarray(v[n_halo:]) for k, v in local.items()}
-    gathered = [None] * world if rank == dst else None
-    dist.gather_object(own, gathered, dst=dst)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    lens = [e - s for s, e in shard_bounds(n_total, world)]
+    longest = max(lens) if lens else 0
+    out = {}
+    for k in sorted(local):
+        own = torch.from_numpy(np.ascontiguousarray(local[k][n_halo:])).to(device)
+        assert own.shape[0] == lens[rank], (k, own.shape, lens[rank])
+        pad = torch.zeros((longest,) + tuple(own.shape[1:]), dtype=own.dtype, device=device)
+        pad[:own.shape[0]] = own
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, bufs, dst=dst)
+        if rank == dst:
+            out[k] = torch.cat([b[:n] for b, n in zip(bufs, lens)]).cpu().numpy()
     if rank != dst:
         return None
-    out = {k: np.concatenate([g[k] for g in gathered]) for k in own}
     assert all(len(v) == n_total for v in out.values())
     return out
 
