@@ -36,6 +36,19 @@ fi
   fi
   [ -f $G/${tag}_prof_plane.ncu-rep ] && python tools/ncu_hot_lines.py $G/${tag}_prof_plane.ncu-rep "icp_kernel<(int)128" sonar_slam_b200/libsonarfe.so 14
 } > $P/${rnd}_hot_lines.txt 2>&1 || true
+# per call site (everything inlined below a call site of the kernel's own file folded into it)
+{
+  echo "# per call site: ncu source page joined with nvdisasm -gi (tools/ncu_call_sites.py) -- round $rnd, gpurun tag $tag"
+  td=$(mktemp -d); (cd $td && cuobjdump -xelf all $OLDPWD/sonar_slam_b200/libsonarfe.so > /dev/null 2>&1)
+  [ -f $G/${tag}_prof_icp_config3.ncu-rep ] && { echo "== icp_kernel<512,1,false>, 296 problems of 2 000 x 20 000 points"; python tools/ncu_call_sites.py $G/${tag}_prof_icp_config3.ncu-rep icp_kernel $td/icp.sm_100a.cubin icp_kernelILi512ELi1ELb0 icp.cu 12; }
+  if [ -f $G/${tag}_prof_pipeline.ncu-rep ]; then
+    echo "== icp_kernel<128,6,false>, the front end's class, 1024 frames"; python tools/ncu_call_sites.py $G/${tag}_prof_pipeline.ncu-rep "icp_kernel<(int)128" $td/icp.sm_100a.cubin icp_kernelILi128ELi6ELb0 icp.cu 12
+    echo "== cart_scatter_kernel, 1024 frames"; python tools/ncu_call_sites.py $G/${tag}_prof_pipeline.ncu-rep cart_scatter $td/featx.sm_100a.cubin cart_scatter featx.cu 10
+    echo "== downsample_kernel (frames), 1024 frames"; python tools/ncu_call_sites.py $G/${tag}_prof_pipeline.ncu-rep "downsample#2" $td/cloud.sm_100a.cubin downsample_kernel cloud.cu 12
+  fi
+  [ -f $G/${tag}_prof_plane.ncu-rep ] && { echo "== icp_kernel<128,6,true> (point-to-plane), 1024 frames"; python tools/ncu_call_sites.py $G/${tag}_prof_plane.ncu-rep "icp_kernel<(int)128" $td/icp.sm_100a.cubin icp_kernelILi128ELi6ELb1 icp.cu 10; }
+  rm -rf $td
+} > $P/${rnd}_call_sites.txt 2>&1 || true
 # SASS excerpt: the interior 16-row block of the pipeline's CFAR kernel + the TMA / mbarrier instructions of the library
 {
   echo "# cuobjdump -sass sonar_slam_b200/libsonarfe.so -- cfar_u8_gate4_kernel<SOCA, bits>: one interior 16-row block"
