@@ -119,7 +119,8 @@ class ClockSampler:
         region of a short run can be over before its first line: keep the same load running, untimed, until `n`
         samples are in -- they are still clocks under this workload.  Returns the number of extra load calls."""
         extra, t_end = 0, time.perf_counter() + timeout
-        while self.proc is not None and len(self.lines) < n and time.perf_counter() < t_end:
+        while (self.proc is not None and self.proc.poll() is None and len(self.lines) < n
+               and time.perf_counter() < t_end):
             load()
             extra += 1
         return extra
