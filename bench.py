@@ -31,6 +31,7 @@ what it prints on stdout while communicators come up or go down is diverted to s
 that stdout stays the one JSON line.
 """
 import argparse
+import atexit
 import json
 import os
 import subprocess
@@ -103,7 +104,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.first = gpu_index, None, [], 0
 
     def start(self):
         try:
@@ -111,15 +112,26 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+            atexit.register(self._kill)   # an exception on the way must not leave the poller behind
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def _kill(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()
+
+    def mark(self):
+        """The timed region starts here: lines that arrived earlier (start-up, rendering, warm-up) are not counted.
+        nvidia-smi needs a few hundred ms before its first line (longer with eight of them starting at once), so it is
+        started well before the timed region and only what it prints from here on is reported."""
+        self.first = len(self.lines)
+
     def keep_load_until(self, n, load, timeout=6.0):
-        """nvidia-smi needs a few hundred ms to start (longer with eight of them starting at once) and the timed
-        region of a short run can be over before its first line: keep the same load running, untimed, until `n`
-        samples are in -- they are still clocks under this workload.  Returns the number of extra load calls."""
+        """The timed region of a short run can still be over before `n` lines have arrived since mark(): keep the
+        same load running, untimed, until they are in -- they are still clocks under this workload.  Returns the
+        number of extra load calls."""
         extra, t_end = 0, time.perf_counter() + timeout
-        while (self.proc is not None and self.proc.poll() is None and len(self.lines) < n
+        while (self.proc is not None and self.proc.poll() is None and len(self.lines) - self.first < n
                and time.perf_counter() < t_end):
             load()
             extra += 1
@@ -131,7 +143,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for l in self.lines:
+        for l in self.lines[self.first:]:
             p = [x.strip() for x in l.split(",")]
             if len(p) < 8:
                 continue
@@ -144,7 +156,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "lines_before_timed_region_not_counted": self.first}
 
 
 # ------------------------------------------------------------------------------------ CPU side
@@ -284,6 +296,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this benchmark has no CPU fallback for the product path")
     torch.cuda.set_device(local)
+    clocks = ClockSampler(local)   # started now, counted from clocks.mark() at the start of the timed region
+    clocks.start()
     if world > 1:
         # NCCL's log is left alone (NCCL_DEBUG / NCCL_DEBUG_FILE are whatever the caller set; the driver counts ranks
         # in it).  stdout carries the one JSON line, so what NCCL prints there while the communicators come up (its
@@ -349,8 +363,7 @@ def run_ours(args):
     for _ in range(W):
         fe.run_dev(frames_dev.data_ptr(), poses, F)
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks.mark()
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

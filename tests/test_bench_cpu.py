@@ -61,3 +61,25 @@ def test_clock_sampler_keeps_the_load_until_samples_arrive(tmp_path, monkeypatch
     extra = c.keep_load_until(3, lambda: time.sleep(0.01))
     out = c.stop()
     assert extra > 0 and out["samples"] >= 3 and out["sm_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+
+
+def test_clock_sampler_counts_only_lines_after_the_mark(tmp_path, monkeypatch):
+    """The sampler is started before the data is rendered (nvidia-smi's start-up is over when the timed region
+    begins); what it printed before mark() -- idle clocks -- is not part of the report."""
+    import stat
+    import time
+    import bench
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nfor i in 1 2 3; do echo '0, 120, 1965, 90.0, Not Active, Not Active, Not Active, "
+                    "Not Active'; sleep 0.03; done\nsleep 0.3\nwhile true; do echo '0, 1965, 1965, 700.0, Not Active, "
+                    "Not Active, Not Active, Not Active'; sleep 0.03; done\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{tmp_path}:" + __import__("os").environ["PATH"])
+    c = bench.ClockSampler(0)
+    c.start()
+    time.sleep(0.25)          # "rendering + warm-up": the three idle lines arrive
+    c.mark()
+    c.keep_load_until(3, lambda: time.sleep(0.01))
+    out = c.stop()
+    assert out["lines_before_timed_region_not_counted"] == 3
+    assert out["samples"] >= 3 and out["sm_mhz"] == 1965.0 and out["reasons"] == []
