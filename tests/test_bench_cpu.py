@@ -83,3 +83,25 @@ def test_clock_sampler_counts_only_lines_after_the_mark(tmp_path, monkeypatch):
     out = c.stop()
     assert out["lines_before_timed_region_not_counted"] == 3
     assert out["samples"] >= 3 and out["sm_mhz"] == 1965.0 and out["reasons"] == []
+
+
+def test_rank_binding_near_its_gpu(tmp_path):
+    """bench.py under torchrun: a rank restricts itself to its GPU's local CPUs (sysfs local_cpulist) before it pins
+    host memory; without the entry, or when the list is not narrower than what it may use, nothing changes."""
+    import os
+    import bench
+    assert bench.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and bench.parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    try:
+        assert bench.bind_near_gpu(0, 0x1b, 0, sysfs=str(tmp_path))["bound"] is False          # no such device
+        dev = tmp_path / "0000:1b:00.0"
+        dev.mkdir()
+        (dev / "local_cpulist").write_text(",".join(map(str, sorted(before))) + "\n")
+        assert bench.bind_near_gpu(0, 0x1b, 0, sysfs=str(tmp_path))["bound"] is False          # not narrower
+        if len(before) > 1:
+            one = sorted(before)[0]
+            (dev / "local_cpulist").write_text(f"{one},100000\n")
+            r = bench.bind_near_gpu(0, 0x1b, 0, sysfs=str(tmp_path))
+            assert r["bound"] and r["cpus"] == 1 and os.sched_getaffinity(0) == {one}
+    finally:
+        os.sched_setaffinity(0, before)
