@@ -124,3 +124,71 @@ def test_icp_failure_messages_and_guess_passthrough():
     bad[0, 0] = 1.2
     assert orc.icp(src, tgt, bad)["status"] == 5
     assert orc.icp(np.zeros((0, 2), np.float32), tgt)["message"] == "no outlier to filter"
+
+
+# ------------------------------------------------------------------ downsample: a second, literal implementation
+def _py_quadtree_medoid(pts, resolution):
+    """Independent restatement of libpointmatcher's OctreeGridDataPointsFilter (samplingMethod 3) as the SURVEY
+    describes it, written recursively over Python lists with numpy float32 scalars: bounding square, split while
+    2*radius > resolution and more than one point, children by (x > cx) | (y > cy) << 1 visited in index order,
+    medoid = first minimum of the sequential float32 sums of Euclidean distances.  Shares no code with
+    oracle/cloud_ref.c (which partitions index ranges in place)."""
+    f = np.float32
+    pts = np.asarray(pts, np.float32)
+    if len(pts) == 0:
+        return []
+    mn, mx = pts.min(0), pts.max(0)
+    rad = mx - mn                                   # float32
+    cx, cy = mn[0] + rad[0] * f(0.5), mn[1] + rad[1] * f(0.5)
+    radius = (rad[0] if rad[0] >= rad[1] else rad[1]) * f(0.5)
+    out = []
+
+    def leaf(members):
+        p = pts[members]
+        dx = p[:, None, 0] - p[None, :, 0]
+        dy = p[:, None, 1] - p[None, :, 1]
+        d = np.sqrt(dx * dx + dy * dy)              # float32, one rounding per operation
+        acc = np.zeros(len(members), np.float32)
+        for b in range(len(members)):               # sequential accumulation in member order
+            acc = acc + d[:, b]
+        out.append(members[int(np.argmin(acc))])    # argmin: first minimum
+
+    def build(members, cx, cy, radius):
+        if not members:
+            return
+        if float(radius) * 2.0 <= float(f(resolution)) or len(members) <= 1:
+            leaf(members)
+            return
+        kids = [[], [], [], []]
+        for i in members:
+            kids[int(pts[i, 0] > cx) | (int(pts[i, 1] > cy) << 1)].append(i)
+        hr = radius * f(0.5)
+        for k in range(4):
+            build(kids[k], cx + (hr if k & 1 else -hr), cy + (hr if k & 2 else -hr), hr)
+
+    build(list(range(len(pts))), cx, cy, radius)
+    return out
+
+
+def _sonar_like_cloud(rng, n):
+    """Wall samples on a pixel lattice (many exact coordinate ties, like the Cartesian pixel centres of the feature
+    node) plus scattered outliers."""
+    t = rng.uniform(0, 1, n)
+    a = np.c_[3 + 20 * t, -8 + 10 * t + rng.normal(0, 0.2, n)]
+    b = np.c_[rng.uniform(0, 30, n // 4), rng.uniform(-27, 27, n // 4)]
+    p = np.concatenate([a, b])
+    return (np.round(p / 0.0586) * 0.0586).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_downsample_equals_a_literal_recursive_quadtree(seed):
+    rng = np.random.default_rng(100 + seed)
+    clouds = [_sonar_like_cloud(rng, 400), rng.uniform(-5, 5, (300, 2)).astype(np.float32),
+              np.c_[np.linspace(0, 9, 200), np.zeros(200)].astype(np.float32),            # a line: zero extent in y
+              np.repeat(rng.uniform(0, 3, (20, 2)), 5, 0).astype(np.float32)]              # coincident points
+    for pts in clouds:
+        for res in (0.5, 0.1, 2.0):
+            out, idx = orc.downsample(pts, res)
+            want = _py_quadtree_medoid(pts, res)
+            assert idx.tolist() == want, (seed, len(pts), res)
+            assert np.array_equal(out, pts[want])
