@@ -90,3 +90,86 @@ def test_compressed_ping_is_decoded_like_the_reference():
         fe.ping_image(types.SimpleNamespace(ping=types.SimpleNamespace(data=b"not an image")))
     fe.compressed_images = False
     assert np.array_equal(fe.ping_image(types.SimpleNamespace(ping=img)), img)
+
+
+# ------------------------------------------------------------------ the ctypes binding against the header, entry by entry
+def _header_text():
+    text = open(os.path.join(REPO, "include", "sonarfe.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.sub(r"//[^\n]*", "", text)
+
+
+def _kind(decl):
+    """'const float *pts' -> 'ptr', 'double tau' -> 'f64', ...  (what a ctypes argtype must be compatible with)"""
+    if "*" in decl:
+        return "ptr"
+    base = decl.replace("const", "").split()
+    base = " ".join(base[:-1]) if len(base) > 1 else base[0]       # drop the parameter name
+    return {"int": "i32", "int32_t": "i32", "float": "f32", "double": "f64", "uint64_t": "u64", "int64_t": "i64"}[base]
+
+
+def _ctypes_kind(t):
+    import ctypes
+    if t is ctypes.c_void_p or t is ctypes.c_char_p or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+        return "ptr"
+    return {ctypes.c_int: "i32", ctypes.c_int32: "i32", ctypes.c_float: "f32", ctypes.c_double: "f64",
+            ctypes.c_uint64: "u64", ctypes.c_int64: "i64"}[t]
+
+
+def test_ctypes_signatures_agree_with_the_header_parameter_by_parameter():
+    """Every entry point the Python side types (argtypes) has the header's parameter count and, position by position,
+    the header's kind (pointer / int / float / double / 64-bit); a binding that drifted from include/sonarfe.h would
+    pass garbage without any error at call time."""
+    import ctypes
+    from sonar_slam_b200 import _lib
+    lib = _lib.load()
+    protos = re.findall(r"SFE_API\s+([^;]*?)\b(sfe_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", _header_text(), flags=re.S)
+    assert len(protos) >= 40
+    typed = 0
+    for ret, name, params in protos:
+        fn = getattr(lib, name)
+        decls = [" ".join(p.split()) for p in params.split(",")]
+        want = [] if decls == ["void"] else [_kind(d) for d in decls]
+        if fn.argtypes is not None:
+            got = [_ctypes_kind(t) for t in fn.argtypes]
+            assert got == want, (name, got, want)
+            typed += 1
+        else:
+            assert want == [], f"{name} takes arguments but has no argtypes"
+        ret = " ".join(ret.split())
+        if ret == "int":
+            assert fn.restype is ctypes.c_int, name
+        elif ret == "void":
+            assert fn.restype is None, name
+        elif ret == "uint64_t":
+            assert fn.restype is ctypes.c_uint64, name
+        elif ret == "const char *":
+            assert fn.restype is ctypes.c_char_p, name
+        else:
+            raise AssertionError(f"unexpected return type {ret!r} of {name}")
+    assert typed >= 38
+
+
+def _header_struct_fields(name):
+    body = re.search(r"typedef struct \{([^}]*)\}\s*" + name + r"\s*;", _header_text(), flags=re.S).group(1)
+    fields = []
+    for stmt in body.split(";"):
+        stmt = " ".join(stmt.split())
+        if not stmt:
+            continue
+        typ, names = stmt.split(" ", 1)
+        fields += [(n.strip(), typ) for n in names.split(",")]
+    return fields
+
+
+def test_ctypes_structures_agree_with_the_header_field_by_field():
+    import ctypes
+    from sonar_slam_b200 import _lib
+    from oracle import oracle as orc
+    ctype_of = {"int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "sfe_icp_params": _lib.IcpParams}
+    for cls, cname in ((_lib.IcpParams, "sfe_icp_params"), (_lib.FrontendParams, "sfe_frontend_params")):
+        want = [(n, ctype_of[t]) for n, t in _header_struct_fields(cname)]
+        assert [(n, t) for n, t in cls._fields_] == want, cname
+    # the oracle's parameter block mirrors the product's (tests hand the same values to both)
+    assert [(n, t) for n, t in orc.IcpParams._fields_] == [(n, t) for n, t in _lib.IcpParams._fields_]
+    assert ctypes.sizeof(_lib.IcpParams) == 40
